@@ -1,0 +1,36 @@
+/* common.cuh -- shared device-side helpers for the sm_100a kernels */
+#ifndef JDB_COMMON_CUH
+#define JDB_COMMON_CUH
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef JDB_SIMT_EMU
+	/* CPU debugging build, see tests/simt/simt_emu.h (test infrastructure) */
+	#include "simt_emu.h"
+#else
+	#include <cuda_runtime.h>
+	#define JDB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+		kernel<<<(grid), (block), (smem), (cudaStream_t) (stream)>>>(__VA_ARGS__)
+	#define JDB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+#include "jdb_device.h"
+
+#define JDB_FULL_MASK 0xffffffffu
+
+/* set by runtime.cu / runtime_emu.cpp */
+extern "C" int  jdb_rt_check_launch(const char* what);
+extern "C" void jdb_rt_set_error(const char* fmt, ...);
+
+static __device__ __forceinline__ unsigned jdb_lane() { return threadIdx.x & 31u; }
+static __device__ __forceinline__ unsigned jdb_warp() { return threadIdx.x >> 5; }
+
+/* unaligned little-endian 32 bit read assembled from two aligned words */
+static __device__ __forceinline__ uint32_t jdb_ld32u(const uint8_t* base, uint32_t off)
+{
+	const uint32_t* w = (const uint32_t*) (base + (off & ~3u));
+	return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
+}
+
+#endif
