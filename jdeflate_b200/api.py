@@ -103,44 +103,44 @@ class JDeflateLib:
                 "jdeflate_b200 has no CPU fallback")
         lib = self.lib = C.CDLL(self.path, mode=C.RTLD_LOCAL)
         P = C.POINTER
-        lib.deflator_create.restype = P(TCodec)
-        lib.deflator_create.argtypes = [C.c_size_t, C.c_ssize_t, C.c_void_p]
-        lib.deflator_destroy.argtypes = [P(TCodec)]
-        lib.deflator_deflate.restype = C.c_int
-        lib.deflator_deflate.argtypes = [P(TCodec), C.c_int]
-        lib.deflator_setdctnr.argtypes = [P(TCodec), C.c_void_p, C.c_size_t]
-        lib.deflator_reset.argtypes = [P(TCodec)]
-        lib.inflator_create.restype = P(TCodec)
-        lib.inflator_create.argtypes = [C.c_size_t, C.c_void_p]
-        lib.inflator_destroy.argtypes = [P(TCodec)]
-        lib.inflator_inflate.restype = C.c_int
-        lib.inflator_inflate.argtypes = [P(TCodec), C.c_uint32]
-        lib.inflator_setdctnr.argtypes = [P(TCodec), C.c_void_p, C.c_size_t]
-        lib.inflator_reset.argtypes = [P(TCodec)]
-        lib.zstrm_create.restype = P(TZStrm)
-        lib.zstrm_create.argtypes = [C.c_size_t, C.c_ssize_t, C.c_void_p]
-        lib.zstrm_destroy.argtypes = [P(TZStrm)]
-        lib.zstrm_setsource.argtypes = [P(TZStrm), C.c_void_p, C.c_size_t]
-        lib.zstrm_setsourcefn.argtypes = [P(TZStrm), IFN, C.c_void_p]
-        lib.zstrm_settargetfn.argtypes = [P(TZStrm), OFN, C.c_void_p]
-        lib.zstrm_setdctnr.argtypes = [P(TZStrm), C.c_void_p, C.c_size_t]
-        lib.zstrm_inflate.restype = C.c_size_t
-        lib.zstrm_inflate.argtypes = [P(TZStrm), C.c_void_p, C.c_size_t]
-        lib.zstrm_deflate.restype = C.c_size_t
-        lib.zstrm_deflate.argtypes = [P(TZStrm), C.c_void_p, C.c_size_t]
-        lib.zstrm_flush.argtypes = [P(TZStrm), C.c_uint32]
-        lib.zstrm_reset.argtypes = [P(TZStrm)]
-        lib.zstrm_crc32update.restype = C.c_uint32
-        lib.zstrm_crc32update.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t]
-        lib.zstrm_adler32update.restype = C.c_uint32
-        lib.zstrm_adler32update.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t]
-        lib.jdeflate_getversion.restype = JDVersion
-        # the reference object lacks zstrm_crc32combine (SURVEY defect 4)
-        for name in ("zstrm_crc32combine", "crc32_ncombine"):
-            fn = getattr(lib, name, None)
-            if fn is not None:
-                fn.restype = C.c_uint32
-                fn.argtypes = [C.c_uint32, C.c_uint32, C.c_size_t if name == "zstrm_crc32combine" else C.c_uint32]
+        self.missing = []
+
+        def bind(name, restype, argtypes):
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                self.missing.append(name)
+                return
+            fn.restype = restype
+            fn.argtypes = argtypes
+
+        bind("deflator_create", P(TCodec), [C.c_size_t, C.c_ssize_t, C.c_void_p])
+        bind("deflator_destroy", None, [P(TCodec)])
+        bind("deflator_deflate", C.c_int, [P(TCodec), C.c_int])
+        bind("deflator_setdctnr", None, [P(TCodec), C.c_void_p, C.c_size_t])
+        bind("deflator_reset", None, [P(TCodec)])
+        bind("inflator_create", P(TCodec), [C.c_size_t, C.c_void_p])
+        bind("inflator_destroy", None, [P(TCodec)])
+        bind("inflator_inflate", C.c_int, [P(TCodec), C.c_uint32])
+        bind("inflator_setdctnr", None, [P(TCodec), C.c_void_p, C.c_size_t])
+        bind("inflator_reset", None, [P(TCodec)])
+        bind("zstrm_create", P(TZStrm), [C.c_size_t, C.c_ssize_t, C.c_void_p])
+        bind("zstrm_destroy", None, [P(TZStrm)])
+        bind("zstrm_setsource", None, [P(TZStrm), C.c_void_p, C.c_size_t])
+        bind("zstrm_setsourcefn", None, [P(TZStrm), IFN, C.c_void_p])
+        bind("zstrm_settargetfn", None, [P(TZStrm), OFN, C.c_void_p])
+        bind("zstrm_setdctnr", None, [P(TZStrm), C.c_void_p, C.c_size_t])
+        bind("zstrm_inflate", C.c_size_t, [P(TZStrm), C.c_void_p, C.c_size_t])
+        bind("zstrm_deflate", C.c_size_t, [P(TZStrm), C.c_void_p, C.c_size_t])
+        bind("zstrm_flush", None, [P(TZStrm), C.c_uint32])
+        bind("zstrm_reset", None, [P(TZStrm)])
+        bind("zstrm_crc32update", C.c_uint32, [C.c_uint32, C.c_void_p, C.c_size_t])
+        bind("zstrm_adler32update", C.c_uint32, [C.c_uint32, C.c_void_p, C.c_size_t])
+        bind("jdeflate_getversion", JDVersion, [])
+        # the reference object lacks zstrm_crc32combine (SURVEY defect 4) and
+        # exports crc32_ncombine instead; the product exports both
+        bind("zstrm_crc32combine", C.c_uint32, [C.c_uint32, C.c_uint32, C.c_size_t])
+        bind("crc32_ncombine", C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint32])
 
     def has(self, name: str) -> bool:
         return hasattr(self.lib, name)

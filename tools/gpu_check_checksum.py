@@ -1,3 +1,4 @@
+import sys, pathlib; sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
 import zlib, os, time, ctypes
 import torch
 from jdeflate_b200 import api
