@@ -1,0 +1,78 @@
+/*
+ * jdeflate/b200.h -- ADDITIVE entry points of the B200-native build.
+ *
+ * Nothing here exists in the reference; nothing in the reference API changes.
+ * These calls express what the single-stream, synchronous jdeflate API cannot
+ * (last row): decoding a batch of independent streams in
+ * one launch, and choosing the CUDA device.
+ *
+ * All pointers may be host or device (cudaMalloc) addresses; device-resident
+ * arguments are used in place, host ones are staged.
+ */
+#ifndef JDB200_JDEFLATE_B200_H
+#define JDB200_JDEFLATE_B200_H
+
+#include <ctoolbox/ctoolbox.h>
+#include <jdeflate/config/config.h>
+#include <jdeflate/inflator.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* container of every stream in a batch */
+typedef enum {
+	JDB200_RAW  = 0,     /* raw DEFLATE (what inflator_inflate decodes)          */
+	JDB200_ZLIB = 1      /* RFC 1950: 2 byte header, Adler-32 trailer (verified) */
+} eJDB200Format;
+
+/* one stream: byte ranges relative to the batch base pointers */
+typedef struct TJDB200Item {
+	uint64 srcoffset;
+	uint64 tgtoffset;
+	uint64 srcsize;
+	uint64 tgtsize;
+} TJDB200Item;
+
+/*
+ * Outcome of one stream, same meaning as a fresh TInflator fed the stream with
+ * final = 1: `status` is an eINFLTResult, `error` an eINFLTError.  `zerror` is
+ * 0 or a ZSTRM_E* code for container problems (ZSTRM_EBADDATA bad header /
+ * missing trailer, ZSTRM_ECHECKSUM, ZSTRM_EMISSINGDICT).
+ */
+typedef struct TJDB200Result {
+	uint32 status;
+	uint32 error;
+	uint32 zerror;
+	uint32 checksum;     /* Adler-32 of the output for JDB200_ZLIB */
+	uint64 srcused;      /* trailer included */
+	uint64 tgtused;
+} TJDB200Result;
+
+/*
+ * Decode `count` independent streams, one GPU warp per stream.
+ * Returns 0 when the batch ran (look at the per stream results), non-zero for
+ * a runtime failure (no device, out of memory).
+ */
+JDEFLATE_API
+int jdb200_inflate_batch(const uint8* source, uint8* target,
+                         const TJDB200Item* items, TJDB200Result* results,
+                         uintxx count, eJDB200Format format);
+
+/* CUDA device used by instances created afterwards by this thread's process
+ * (default: $JDB200_DEVICE, else $LOCAL_RANK, else 0) */
+JDEFLATE_API
+int jdb200_set_device(int ordinal);
+
+JDEFLATE_API
+int jdb200_device_count(void);
+
+/* last runtime error text of the calling thread ("" when none) */
+JDEFLATE_API
+const char* jdb200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -80,6 +80,68 @@ int jdb_checksum(const uint8_t* data, size_t n, int which,
                  uint32_t* crc_io, uint32_t* adler_io,
                  void* work, jdb_stream s);
 
+
+/* ---- inflate (inflate.cu) ---------------------------------------------- */
+#define JDB_INFLATE_HISTORY 32768u     /* DEFLATE window, power of two */
+#define JDB_INF_LIT_TABLE   1344       /* >= ENOUGHL 1332 (root 10), reference src/inflator.c:35-48 */
+#define JDB_INF_DIST_TABLE  416        /* >= ENOUGHD 400  (root 8),  reference src/inflator.c:50-62 */
+
+enum { JDB_INF_HEADER = 0, JDB_INF_STORED = 1, JDB_INF_SYMBOLS = 2 };
+enum { JDB_FMT_RAW = 0, JDB_FMT_ZLIB = 1 };
+/* container level problems use the ZSTRM_E* numbering of jdeflate/zstrm.h */
+enum { JDB_ZERR_BADDATA = 3, JDB_ZERR_CHECKSUM = 4, JDB_ZERR_MISSINGDICT = 6 };
+
+/* one stream of a batch: byte ranges relative to the two base pointers */
+typedef struct jdb_inflate_item {
+	uint64_t src_off;
+	uint64_t dst_off;
+	uint64_t src_len;
+	uint64_t dst_cap;
+} jdb_inflate_item;
+
+/* per stream outcome: INFLT_* status / error codes of jdeflate/inflator.h */
+typedef struct jdb_inflate_result {
+	uint32_t status;
+	uint32_t error;
+	uint32_t zerror;      /* 0 or JDB_ZERR_* (container formats only) */
+	uint32_t checksum;    /* Adler-32 of the output (JDB_FMT_ZLIB)    */
+	uint64_t consumed;    /* source bytes used, trailer included      */
+	uint64_t produced;
+} jdb_inflate_result;
+
+/*
+ * Device resident state of a resumable (streaming) decode: what the reference
+ * keeps in TINFLTPrvt between inflator_inflate calls (src/inflator.c:73-149):
+ * bit buffer, position in the block structure, a match cut by the end of the
+ * target, the tables of the block in progress and the last 32 KiB of output.
+ */
+typedef struct jdb_inflate_state {
+	uint64_t bitbuf;
+	uint64_t total_out;       /* absolute output position (ring index base) */
+	uint64_t hist_avail;      /* bytes of history usable as match source    */
+	uint32_t bitcnt;
+	uint32_t phase;           /* JDB_INF_*                                   */
+	uint32_t lastblock;
+	uint32_t stored_left;
+	uint32_t pend_len;
+	uint32_t pend_dist;
+	uint32_t lit[JDB_INF_LIT_TABLE];
+	uint32_t dist[JDB_INF_DIST_TABLE];
+	uint8_t  history[JDB_INFLATE_HISTORY];
+} jdb_inflate_state;
+
+/*
+ * Decode `count` independent streams, one warp each (dynamic assignment).
+ *   states   NULL for one-shot streams; else one jdb_inflate_state per stream
+ *            (zero-initialised before the first call) for resumable decoding
+ *   final    non-zero: running out of input is INFLT_EINPUTEND, not SRCEXHSTD
+ *   counter  device u32 scratch (work distribution)
+ */
+int jdb_inflate_batch(const uint8_t* src_base, uint8_t* dst_base,
+                      const jdb_inflate_item* items, jdb_inflate_result* results,
+                      jdb_inflate_state* states, uint32_t count, uint32_t format,
+                      uint32_t final, uint32_t* counter, jdb_stream s);
+
 #ifdef __cplusplus
 }
 #endif
