@@ -41,6 +41,9 @@
 #define LIT_TABLE        JDB_INF_LIT_TABLE
 #define DIST_TABLE       JDB_INF_DIST_TABLE
 #define QUEUE            32
+#define RING             4096u     /* per-warp window of the newest output bytes */
+#define MAXBATCH         1024u     /* a batch stops growing beyond this many bytes  */
+#define RING_KEEP        (RING - MAXBATCH - 258u)
 
 /* table entry: value<<16 | type<<8 | extra<<4 | nbits   (nbits==0: invalid) */
 #define T_LIT   0u
@@ -89,6 +92,7 @@ struct WarpMem {
 	uint16_t count[16];
 	uint16_t next[16];
 	uint32_t scratch[8];
+	uint8_t  ring[RING];
 };
 
 enum { KIND_LIT = 0, KIND_DIST = 1, KIND_PRE = 2 };
@@ -274,27 +278,50 @@ struct Stream {
 	uint64_t consumed;          /* source bytes used by this call */
 	uint64_t hist_avail;        /* bytes available before dst[0] (history / dictionary) */
 	uint64_t total_before;      /* absolute output position of dst[0] (ring index base) */
+	uint8_t* ring;              /* shared-memory copy of the newest RING output bytes */
+	int64_t  ring_lo;           /* positions >= ring_lo are served from the ring */
 	uint32_t status, error;
 };
 
-/* byte at output position `pos` relative to this call's dst; negative
- * positions come from the history ring of earlier calls */
+/* byte at output position `pos` relative to this call's dst: the newest bytes
+ * come from the shared-memory ring, older ones from L2, and negative positions
+ * from the history ring of earlier calls */
 static __device__ __forceinline__ uint8_t
 out_byte(const Stream& s, int64_t pos)
 {
+	if (pos >= s.ring_lo) return s.ring[(uint32_t) pos & (RING - 1)];
 	if (pos >= 0) return __ldcg(s.dst + pos);
 	uint64_t abs = s.total_before + (uint64_t) pos;
 	return __ldcg(s.st->history + (abs & (JDB_INFLATE_HISTORY - 1)));
+}
+
+static __device__ __forceinline__ void
+put_byte(const Stream& s, uint64_t pos, uint8_t v)
+{
+	s.dst[pos] = v;
+	s.ring[(uint32_t) pos & (RING - 1)] = v;
 }
 
 /* warp-cooperative copy of `len` bytes with source `dist` back from `pos` */
 static __device__ __forceinline__ void
 copy_match(const Stream& s, uint64_t pos, uint32_t len, uint32_t dist)
 {
+	/* every source byte lies before `pos` (k < dist), so all loads can be
+	 * issued before the first store */
 	const unsigned lane = jdb_lane();
-	for (uint32_t j = lane; j < len; j += 32) {
-		uint32_t k = dist >= len ? j : j % dist;
-		s.dst[pos + j] = out_byte(s, (int64_t) (pos - dist) + k);
+	uint8_t tmp[9];                      /* 258 bytes / 32 lanes */
+#pragma unroll
+	for (int i = 0; i < 9; i++) {
+		uint32_t j = lane + 32u * i;
+		if (j < len) {
+			uint32_t k = dist >= len ? j : j % dist;
+			tmp[i] = out_byte(s, (int64_t) (pos - dist) + k);
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < 9; i++) {
+		uint32_t j = lane + 32u * i;
+		if (j < len) put_byte(s, pos + j, tmp[i]);
 	}
 }
 
@@ -318,6 +345,8 @@ inflate_stream(WarpMem* m, Stream& s)
 	s.error = 0;
 	s.hist_avail = 0;
 	s.total_before = 0;
+	s.ring = m->ring;
+	s.ring_lo = 0;
 
 	if (s.st) {
 		jdb_inflate_state* st = s.st;
@@ -486,7 +515,7 @@ inflate_stream(WarpMem* m, Stream& s)
 			uint64_t srcleft = s.src_len - pos, dstleft = s.dst_cap - s.out;
 			if (n > srcleft) n = srcleft;
 			if (n > dstleft) n = dstleft;
-			for (uint64_t j = lane; j < n; j += 32) s.dst[s.out + j] = s.src[pos + j];
+			for (uint64_t j = lane; j < n; j += 32) put_byte(s, s.out + j, s.src[pos + j]);
 			__syncwarp();
 			s.out += n;
 			stored_left -= (uint32_t) n;
@@ -509,7 +538,7 @@ inflate_stream(WarpMem* m, Stream& s)
 				ev = 0;
 				if (lane == 0) {
 					const uint64_t room = s.dst_cap - s.out;
-					while (nq < QUEUE) {
+					while (nq < QUEUE && qbytes < MAXBATCH) {
 						/* fast path needs an aligned pointer, 8 input bytes and room for a full match */
 						const bool fast = (((uintptr_t) b.p & 3u) == 0) && (b.end - b.p >= 8) &&
 						                  (qbytes + 258 <= room);
@@ -586,6 +615,8 @@ inflate_stream(WarpMem* m, Stream& s)
 						if ((int) lane >= o) incl += t;
 					}
 					const uint64_t base = s.out;
+					s.ring_lo = (int64_t) base - (int64_t) RING_KEEP;
+					if (s.ring_lo < 0) s.ring_lo = 0;
 					const uint64_t pos = base + incl - len;
 					const uint32_t total = __shfl_sync(JDB_FULL_MASK, incl, 31);
 					/* clip the last symbol to the target capacity */
@@ -597,10 +628,16 @@ inflate_stream(WarpMem* m, Stream& s)
 					}
 					const bool dependent = is_match && ((int64_t) pos - (int64_t) dist + (int64_t) len > (int64_t) base || dist < len);
 					const bool longm = is_match && !dependent && emit > 16;
-					if (lane < nq && !is_match) s.dst[pos] = (uint8_t) q;
+					if (lane < nq && !is_match) put_byte(s, pos, (uint8_t) q);
 					if (is_match && !dependent && !longm) {
-						for (uint32_t j = 0; j < emit; j++)
-							s.dst[pos + j] = out_byte(s, (int64_t) (pos - dist) + j);
+						/* short far match: all loads first, then the stores */
+						uint8_t tmp[16];
+#pragma unroll
+						for (int j = 0; j < 16; j++)
+							if ((uint32_t) j < emit) tmp[j] = out_byte(s, (int64_t) (pos - dist) + j);
+#pragma unroll
+						for (int j = 0; j < 16; j++)
+							if ((uint32_t) j < emit) put_byte(s, pos + j, tmp[j]);
 					}
 					unsigned lm = __ballot_sync(JDB_FULL_MASK, longm);
 					while (lm) {

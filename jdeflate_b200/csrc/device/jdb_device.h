@@ -142,6 +142,46 @@ int jdb_inflate_batch(const uint8_t* src_base, uint8_t* dst_base,
                       jdb_inflate_state* states, uint32_t count, uint32_t format,
                       uint32_t final, uint32_t* counter, jdb_stream s);
 
+/* ---- deflate pipeline stages (lz.cu, huffman.cu, pack.cu) ---------------- */
+#define JDB_SEG 16384u      /* LZ segment: positions per CTA, histogram granule */
+
+/* links to the previous same-hash position (u16 distance, 0 = none), one per
+ * input byte; `range` (divides chunk_bytes) is the work item of one warp */
+int jdb_lz_chain(const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint32_t range,
+                 uint16_t* prev, jdb_stream s);
+
+/* match search + parse: tokens of segment k at tok[k*JDB_SEG ...), their count
+ * in seg_ntok[k], the 320-bin symbol histogram in seg_hist[k*320 ...) */
+int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes, const uint16_t* prev,
+                 uint32_t good, uint32_t nice, uint32_t chain, uint32_t lazy,
+                 uint32_t* tok, uint32_t* seg_ntok, uint32_t* seg_hist, jdb_stream s);
+
+/* per block Huffman code construction + block type choice */
+int jdb_huffman_blocks(const uint32_t* seg_ntok, const uint32_t* seg_hist, uint64_t n,
+                       uint32_t chunk_bytes, uint32_t block_segs, uint32_t nblocks,
+                       uint32_t level, uint32_t fixedonly, void* blocks, jdb_stream s);
+
+/* ---- whole pipeline (deflate.cu) ---------------------------------------- */
+typedef struct jdb_deflate_cfg {
+	uint32_t level;          /* 0..9 (0 = stored only)                              */
+	uint32_t fixedonly;      /* DEFLT_FIXEDCODES                                    */
+	uint32_t good, nice, chain, lazy;   /* reference setparameters(), src/deflator.c:241-263 */
+	uint32_t chunk_bytes;    /* independent chunk, multiple of JDB_SEG              */
+	uint32_t block_segs;     /* segments per DEFLATE block, 1..16                   */
+	uint32_t chain_range;    /* positions per chain-building warp (0: whole chunk)  */
+	uint32_t final;          /* last chunk closes the stream (BFINAL = 1)           */
+} jdb_deflate_cfg;
+
+size_t jdb_deflate_workspace_bytes(uint64_t n, const jdb_deflate_cfg* cfg);
+
+/*
+ * Compress the batch in[0..n) (device memory, 16-byte aligned).  On return
+ * *out points at the compressed bytes inside `work` and *total_dev at the u64
+ * byte count, both valid once the stream has been synchronised.
+ */
+int jdb_deflate_run(const uint8_t* in, uint64_t n, const jdb_deflate_cfg* cfg,
+                    void* work, uint8_t** out, uint64_t** total_dev, jdb_stream s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,389 @@
+/*
+ * lz.cu -- LZ77 stage of the deflate pipeline for sm_100a.
+ *
+ * Replaces the reference's serial parsers compress1 / compress2 with their
+ * match finders getmatch1 / getmatch2 and hash maintenance skipbytes1/2,
+ * slidehash (src/deflator.c:2335-2973, 1899-1911).
+ *
+ * Two kernels:
+ *
+ *  chain_kernel   builds, for every input position, the distance to the
+ *                 previous position with the same 4-byte hash -- exactly the
+ *                 links the reference's insert-every-position policy produces
+ *                 in mchain[] (the chain content does not depend on the parse,
+ *                 only on the data).  One warp per range of a chunk, hash heads
+ *                 in shared memory (2^15 x u16), 32 positions per step resolved
+ *                 with __match_any_sync.  Hash: big-endian 4 bytes * 0x1e35a7bd
+ *                 (gethead/gethash, src/deflator.c:1930-1947), top 15 bits.
+ *
+ *  lz_kernel      one CTA per 16 KiB segment.  The 32 KiB of history plus the
+ *                 segment (bytes and chain links) are staged in shared memory;
+ *                 every thread then walks the chains of its positions
+ *                 (bounded by the level's max chain, early exit at `nice`,
+ *                 the reference's strbgn[len]==pmatch[len] pre-filter) --
+ *                 the search is position-parallel because on the compression
+ *                 side the history is the input itself.  The lazy / greedy
+ *                 selection (good length, the reference's offset-aware accept
+ *                 rule src/deflator.c:2860-2879) is evaluated per position,
+ *                 and the one truly serial step -- following the chosen tokens
+ *                 from the segment start -- is done by 64 speculative walkers
+ *                 whose paths are stitched exactly (paths re-converge within a
+ *                 few tokens).  Tokens are compacted with a block scan and
+ *                 written coalesced; symbol histograms are accumulated with
+ *                 shared-memory atomics.
+ *
+ * Algorithmic traffic of the stage: N bytes read.  Implementation traffic per
+ * input byte: 2 B links written + (1+2)*3 B staged per segment (history halo)
+ * + <= 4 B tokens written.
+ */
+#include "deflate.cuh"
+
+#define HASH_BITS      15
+#define HASH_MUL       0x1e35a7bdu
+
+/* ---------------------------------------------------------------------------
+ * chain_kernel
+ * ------------------------------------------------------------------------- */
+
+/*
+ * Work item r covers positions [r*range, (r+1)*range) of the batch; ranges
+ * never straddle chunks (range divides the chunk size).  A range that does not
+ * start a chunk first replays the preceding 32 KiB without emitting links.
+ */
+__global__ void __launch_bounds__(32)
+chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t range,
+             uint16_t* __restrict__ prev)
+{
+	JDB_DYN_SMEM(smem_raw);
+	uint16_t* head = (uint16_t*) smem_raw;          /* 2^15 entries */
+	const unsigned lane = threadIdx.x;
+
+	const uint64_t r0 = (uint64_t) blockIdx.x * range;
+	if (r0 >= n) return;
+	const uint64_t chunk0 = r0 / chunk_bytes * chunk_bytes;
+	uint64_t chunk1 = chunk0 + chunk_bytes;
+	if (chunk1 > n) chunk1 = n;
+	uint64_t r1 = r0 + range;
+	if (r1 > chunk1) r1 = chunk1;
+	uint64_t start = r0 >= chunk0 + WND ? r0 - WND : chunk0;   /* warm-up start */
+
+	/* positions are handled relative to `start`; an entry holds the low 16
+	 * bits, "empty" is anything that decodes to a distance >= 32768 */
+	for (uint32_t i = lane; i < (1u << HASH_BITS); i += 32) head[i] = 0x8000u;
+	__syncwarp();
+
+	const uint64_t last_hashable = chunk1 >= 4 ? chunk1 - 4 : 0;   /* inclusive; needs chunk1 >= 4 */
+	for (uint64_t base = start; base < r1; base += 32) {
+		const uint32_t rel = (uint32_t) (base - start);
+		if (rel && (rel & (WND - 1)) == 0) {
+			/* every 32768 positions retire entries that are out of the window
+			 * so 16-bit positions never alias (cf. slidehash) */
+			const uint32_t stale = (rel + 0x8000u) & 0xffffu;
+			for (uint32_t i = lane; i < (1u << HASH_BITS); i += 32) {
+				uint32_t d = (rel - head[i]) & 0xffffu;
+				if (d >= WND) head[i] = (uint16_t) stale;
+			}
+			__syncwarp();
+		}
+		const uint64_t p = base + lane;
+		const bool valid = chunk1 >= 4 && p <= last_hashable;
+		uint32_t h = 0xffffffffu - lane;                 /* unique per lane when invalid */
+		if (valid) {
+			const uint8_t* q = in + p;
+			uint32_t be = ((uint32_t) q[0] << 24) | ((uint32_t) q[1] << 16) | ((uint32_t) q[2] << 8) | q[3];
+			h = (be * HASH_MUL) >> (32 - HASH_BITS);
+		}
+		const unsigned same = __match_any_sync(JDB_FULL_MASK, h);
+		uint32_t dist = 0;
+		if (valid) {
+			const unsigned lower = same & ((1u << lane) - 1u);
+			if (lower) {
+				dist = lane - (31 - __clz(lower));
+			} else {
+				uint32_t d = ((rel + lane) - head[h]) & 0xffffu;
+				if (d < WND && d <= rel + lane) dist = d;
+			}
+		}
+		__syncwarp();
+		if (valid && (same >> lane) == 1u) head[h] = (uint16_t) (rel + lane);   /* highest lane of its group */
+		if (p >= r0 && p < r1) prev[p] = (uint16_t) dist;
+		__syncwarp();
+	}
+}
+
+/* ---------------------------------------------------------------------------
+ * lz_kernel
+ * ------------------------------------------------------------------------- */
+
+#define LZ_THREADS   1024
+#define PER_THREAD   (SEG / LZ_THREADS)            /* 16 */
+#define WALK_BLOCK   256u
+#define WALKERS      (SEG / WALK_BLOCK)            /* 64 */
+#define DATA_BYTES   (WND + SEG + 320)             /* history + segment + look-ahead/guard */
+
+struct LzParams {
+	uint32_t good, nice, chain, lazy;
+};
+
+struct LzSmem {
+	uint32_t m[SEG];                 /* per position result, later flags      */
+	uint16_t prev[WND + SEG];
+	uint8_t  data[DATA_BYTES];
+	uint32_t spec[SEG / 32];         /* positions on the speculative paths    */
+	uint32_t fix[SEG / 32];          /* positions added by the stitching pass */
+	uint32_t hist[NSYM];
+	uint32_t land[WALKERS];          /* where each walker left its block      */
+	uint32_t merge[WALKERS];
+	uint32_t warp_sum[LZ_THREADS / 32];
+};
+
+static __device__ __forceinline__ uint32_t ilog2_u32(uint32_t v) { return 31 - __clz(v); }
+
+/* the token decision for a fresh position p (segment coordinates): returns
+ * the next fresh position */
+static __device__ __forceinline__ uint32_t
+next_pos(const uint32_t* m, uint32_t p)
+{
+	uint32_t v = m[p];
+	return (v & M_TAKE) ? p + ((v >> 16) & 0x1ffu) : p + 1;
+}
+
+__global__ void __launch_bounds__(LZ_THREADS, 1)
+lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
+          const uint16_t* __restrict__ prev, LzParams prm,
+          uint32_t* __restrict__ tok, uint32_t* __restrict__ seg_ntok, uint32_t* __restrict__ seg_hist)
+{
+	JDB_DYN_SMEM(smem_raw);
+	LzSmem& S = *(LzSmem*) smem_raw;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t seg = blockIdx.x;
+
+	const uint64_t seg0 = (uint64_t) seg * SEG;
+	const uint64_t chunk0 = seg0 / chunk_bytes * chunk_bytes;
+	uint64_t chunk1 = chunk0 + chunk_bytes;
+	if (chunk1 > n) chunk1 = n;
+	uint64_t seg1 = seg0 + SEG;
+	if (seg1 > chunk1) seg1 = chunk1;
+	const uint32_t seg_len = (uint32_t) (seg1 - seg0);
+	const uint64_t hist0 = seg0 >= chunk0 + WND ? seg0 - WND : chunk0;    /* first staged byte */
+	const uint32_t hoff = (uint32_t) (seg0 - hist0);                      /* segment start in smem coords */
+
+	/* ---- stage bytes and links (16-byte vectors; `in` and hist0 are 16-aligned) ---- */
+	{
+		const uint32_t nbytes = (uint32_t) ((chunk1 - hist0) < (uint64_t) DATA_BYTES ? (chunk1 - hist0) : DATA_BYTES);
+		const uint4* src = (const uint4*) (in + hist0);
+		uint4* dst = (uint4*) S.data;
+		const uint32_t nv = nbytes / 16;
+		for (uint32_t i = tid; i < nv; i += LZ_THREADS) dst[i] = __ldg(src + i);
+		for (uint32_t i = nv * 16 + tid; i < DATA_BYTES; i += LZ_THREADS)
+			S.data[i] = i < nbytes ? in[hist0 + i] : 0;
+		const uint32_t nlinks = hoff + seg_len;
+		const uint4* ps = (const uint4*) (prev + hist0);
+		uint4* pd = (uint4*) S.prev;
+		const uint32_t npv = nlinks / 8;
+		for (uint32_t i = tid; i < npv; i += LZ_THREADS) pd[i] = __ldg(ps + i);
+		for (uint32_t i = npv * 8 + tid; i < nlinks; i += LZ_THREADS) S.prev[i] = prev[hist0 + i];
+		for (uint32_t i = tid; i < SEG / 32; i += LZ_THREADS) { S.spec[i] = 0; S.fix[i] = 0; }
+		for (uint32_t i = tid; i < NSYM; i += LZ_THREADS) S.hist[i] = 0;
+	}
+	__syncthreads();
+
+	/* ---- match search: thread t handles positions t, t+1024, ... ---- */
+	for (uint32_t k = 0; k < PER_THREAD; k++) {
+		const uint32_t p = tid + k * LZ_THREADS;
+		uint32_t result = 0;
+		if (p < seg_len) {
+			const uint32_t j = hoff + p;                                /* smem coordinate */
+			uint32_t maxlen = (uint32_t) (seg1 - (seg0 + p));          /* never past the segment */
+			if (maxlen > MAXLEN) maxlen = MAXLEN;
+			if (maxlen >= MINLEN) {
+				uint32_t best = MINLEN - 1, bestd = 0;
+				uint32_t cur = j, steps = prm.chain;
+				uint32_t d = S.prev[cur];
+				const uint32_t w0 = jdb_ld32u(S.data, j);
+				while (d != 0 && steps-- != 0) {
+					if (d > cur) break;
+					const uint32_t q = cur - d;
+					const uint32_t total = j - q;
+					if (total >= WND) break;
+					/* pre-filter on the byte that would extend the best match */
+					if (S.data[q + best] == S.data[j + best] && jdb_ld32u(S.data, q) == w0) {
+						uint32_t len = 4;
+						while (len < maxlen) {
+							uint32_t x = jdb_ld32u(S.data, j + len) ^ jdb_ld32u(S.data, q + len);
+							if (x) { len += (uint32_t) (__ffs((int) x) - 1) >> 3; break; }
+							len += 4;
+						}
+						if (len > maxlen) len = maxlen;
+						if (len > best) {
+							best = len;
+							bestd = total;
+							if (len >= prm.nice || len == maxlen) break;
+						}
+					}
+					cur = q;
+					d = S.prev[cur];
+				}
+				if (best >= MINLEN) result = (best << 16) | bestd;
+			}
+		}
+		if (p < SEG) S.m[p] = result;
+	}
+	__syncthreads();
+
+	/* ---- per position: would a parser arriving here take the match? ---- */
+	for (uint32_t k = 0; k < PER_THREAD; k++) {
+		const uint32_t p = tid + k * LZ_THREADS;
+		if (p >= seg_len) continue;
+		const uint32_t v = S.m[p] & ~M_TAKE;
+		const uint32_t len = v >> 16;
+		if (len == 0) continue;
+		bool take = true;
+		if (prm.lazy && len < prm.good && p + 1 < seg_len) {
+			const uint32_t w = S.m[p + 1] & ~M_TAKE;
+			const uint32_t nlen = w >> 16;
+			if (nlen >= len) {
+				/* the reference's accept rule, src/deflator.c:2865-2879 */
+				const int32_t delta = (int32_t) nlen - (int32_t) len;
+				if (delta > 4) take = false;
+				else {
+					const int32_t l1 = (int32_t) ilog2_u32(v & 0xffffu), l2 = (int32_t) ilog2_u32(w & 0xffffu);
+					if ((delta << 2) + (l1 - l2) >= 2) take = false;
+				}
+			}
+		}
+		if (take) S.m[p] = v | M_TAKE;
+	}
+	__syncthreads();
+
+	/* ---- speculative walkers: one per 256 positions ---- */
+	if (tid < WALKERS) {
+		const uint32_t b0 = tid * WALK_BLOCK, b1 = b0 + WALK_BLOCK;
+		uint32_t p = b0;
+		if (b0 < seg_len) {
+			const uint32_t lim = b1 < seg_len ? b1 : seg_len;
+			while (p < lim) {
+				S.spec[p >> 5] |= 1u << (p & 31);        /* words of a block belong to one walker */
+				p = next_pos(S.m, p);
+			}
+		}
+		S.land[tid] = p;
+		S.merge[tid] = b0;
+	}
+	__syncthreads();
+
+	/* ---- stitch: thread 0 follows the true path across the walker blocks ---- */
+	if (tid == 0) {
+		uint32_t t = 0;                                   /* true entry position */
+		for (uint32_t w = 0; w < WALKERS; w++) {
+			const uint32_t b0 = w * WALK_BLOCK, b1 = b0 + WALK_BLOCK;
+			if (b0 >= seg_len) break;
+			const uint32_t lim = b1 < seg_len ? b1 : seg_len;
+			if (t >= lim) { S.merge[w] = lim; continue; }          /* block jumped over */
+			if (t == b0) { S.merge[w] = b0; t = S.land[w]; continue; }
+			uint32_t p = t;
+			while (p < lim && !((S.spec[p >> 5] >> (p & 31)) & 1u)) {
+				S.fix[p >> 5] |= 1u << (p & 31);
+				p = next_pos(S.m, p);
+			}
+			if (p < lim) { S.merge[w] = p; t = S.land[w]; }
+			else { S.merge[w] = lim; t = p; }
+		}
+	}
+	__syncthreads();
+
+	/* ---- emit: 16 consecutive positions per thread ---- */
+	{
+		const uint32_t p0 = tid * PER_THREAD;
+		const uint32_t w = p0 / WALK_BLOCK;
+		const uint32_t mg = S.merge[w];
+		uint32_t bits = (S.spec[p0 >> 5] >> (p0 & 31)) & 0xffffu;
+		/* speculative positions count only from the merge point on */
+		if (mg >= p0 + PER_THREAD) bits = 0;
+		else if (mg > p0) bits &= ~((1u << (mg - p0)) - 1u);
+		bits |= (S.fix[p0 >> 5] >> (p0 & 31)) & 0xffffu;
+		if (p0 >= seg_len) bits = 0;
+
+		const uint32_t cnt = (uint32_t) __popc(bits);
+		uint32_t incl = cnt;
+		for (int o = 1; o < 32; o <<= 1) {
+			uint32_t t = __shfl_up_sync(JDB_FULL_MASK, incl, o);
+			if ((int) (tid & 31) >= o) incl += t;
+		}
+		if ((tid & 31) == 31) S.warp_sum[tid >> 5] = incl;
+		__syncthreads();
+		if (tid < 32) {
+			uint32_t v = S.warp_sum[tid];
+			uint32_t iv = v;
+			for (int o = 1; o < 32; o <<= 1) {
+				uint32_t t = __shfl_up_sync(JDB_FULL_MASK, iv, o);
+				if ((int) tid >= o) iv += t;
+			}
+			S.warp_sum[tid] = iv - v;                    /* exclusive */
+			if (tid == 31) seg_ntok[seg] = iv;
+		}
+		__syncthreads();
+		uint32_t o = S.warp_sum[tid >> 5] + incl - cnt;
+		uint32_t* out = tok + seg0;
+		while (bits) {
+			const uint32_t p = p0 + (uint32_t) (__ffs((int) bits) - 1);
+			bits &= bits - 1;
+			const uint32_t v = S.m[p];
+			uint32_t token;
+			if (v & M_TAKE) {
+				const uint32_t len = (v >> 16) & 0x1ffu, dist = v & 0xffffu;
+				token = TOK_MATCH | ((len - 3) << 16) | (dist - 1);
+				atomicAdd(&S.hist[257 + len_symbol(len)], 1u);
+				atomicAdd(&S.hist[DSYM0 + dist_symbol(dist)], 1u);
+			} else {
+				token = S.data[hoff + p];
+				atomicAdd(&S.hist[token], 1u);
+			}
+			out[o++] = token;
+		}
+	}
+	__syncthreads();
+	for (uint32_t i = tid; i < NSYM; i += LZ_THREADS) seg_hist[(uint64_t) seg * NSYM + i] = S.hist[i];
+}
+
+/* ---- launchers ------------------------------------------------------------- */
+
+extern "C" int jdb_lz_chain(const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint32_t range,
+                            uint16_t* prev, jdb_stream s)
+{
+	if (n == 0) return JDB_OK;
+	const size_t smem = sizeof(uint16_t) << HASH_BITS;
+#ifndef JDB_SIMT_EMU
+	static int configured[64];
+	int dev = jdb_rt_get_device();
+	if (dev >= 0 && dev < 64 && !configured[dev]) {
+		cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		configured[dev] = 1;
+	}
+#endif
+	const uint64_t items = (n + range - 1) / range;
+	JDB_LAUNCH(chain_kernel, dim3((unsigned) items), dim3(32), smem, s, in, n, chunk_bytes, range, prev);
+	return jdb_rt_check_launch("chain_kernel");
+}
+
+extern "C" int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes, const uint16_t* prev,
+                            uint32_t good, uint32_t nice, uint32_t chain, uint32_t lazy,
+                            uint32_t* tok, uint32_t* seg_ntok, uint32_t* seg_hist, jdb_stream s)
+{
+	if (n == 0) return JDB_OK;
+	const size_t smem = sizeof(LzSmem);
+#ifndef JDB_SIMT_EMU
+	static int configured[64];
+	int dev = jdb_rt_get_device();
+	if (dev >= 0 && dev < 64 && !configured[dev]) {
+		cudaFuncSetAttribute(lz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		configured[dev] = 1;
+	}
+#endif
+	LzParams prm;
+	prm.good = good; prm.nice = nice; prm.chain = chain; prm.lazy = lazy;
+	const uint64_t nseg = (n + SEG - 1) / SEG;
+	JDB_LAUNCH(lz_kernel, dim3((unsigned) nseg), dim3(LZ_THREADS), smem, s,
+	           in, n, chunk_bytes, prev, prm, tok, seg_ntok, seg_hist);
+	return jdb_rt_check_launch("lz_kernel");
+}
