@@ -17,6 +17,7 @@
 #include <string.h>
 #include <stddef.h>
 #include "jdb_host.h"
+#include "jdb_internal.h"
 
 #define POISON        0xDEADBEEFu
 #define INQ_BYTES     ((size_t) 32 << 20)     /* compressed bytes per launch   */
@@ -53,6 +54,11 @@ struct TINFLTPrvt {
 	/* pinned: item + result; device mirrors */
 	uint8* pinned;
 	uint8* dscratch;
+
+	/* checksums of the produced bytes for zstrm (device side, running) */
+	int       checks;       /* JDB_CK_* mask */
+	uint32_t* dchecks;      /* device: [0] crc register, [1] adler */
+	jdb_dbuf  ckwork;
 };
 
 typedef char jdb_inflator_layout_check[(sizeof(struct TInflator) == sizeof(struct TINFLTPblc)) ? 1 : -1];
@@ -100,7 +106,8 @@ inflator_create(uintxx flags, const TAllocator* allctr)
 	PRVT->dstate = jdb_dev_alloc(sizeof(jdb_inflate_state));
 	PRVT->dscratch = jdb_dev_alloc(256);
 	PRVT->pinned = jdb_pinned_alloc(256);
-	if (PRVT->dstate == NULL || PRVT->dscratch == NULL || PRVT->pinned == NULL) {
+	PRVT->dchecks = jdb_dev_alloc(64);
+	if (PRVT->dstate == NULL || PRVT->dscratch == NULL || PRVT->pinned == NULL || PRVT->dchecks == NULL) {
 		goto L_FAIL;
 	}
 
@@ -133,6 +140,12 @@ inflator_reset(TInflator* state)
 	PRVT->inqoff = 0;
 	PRVT->inqlen = 0;
 
+	{
+		uint32_t* init = (uint32_t*) (PRVT->pinned + 208);
+		init[0] = 0xffffffffu;
+		init[1] = 1u;
+		jdb_copy_async(PRVT->dchecks, init, 8, PRVT->stream);
+	}
 	/* a zeroed state block is "at a block header, no history" */
 	if (jdb_memset_async(PRVT->dstate, 0, offsetof(jdb_inflate_state, lit), PRVT->stream) != JDB_OK) {
 		PBLC->error = INFLT_EOOM;
@@ -153,6 +166,8 @@ inflator_destroy(TInflator* state)
 	}
 	jdb_dbuf_release(&PRVT->inq);
 	jdb_dbuf_release(&PRVT->outbuf);
+	jdb_dbuf_release(&PRVT->ckwork);
+	jdb_dev_free(PRVT->dchecks);
 	jdb_dev_free(PRVT->dstate);
 	jdb_dev_free(PRVT->dscratch);
 	jdb_pinned_free(PRVT->pinned);
@@ -188,6 +203,27 @@ inflator_setdctnr(TInflator* state, const uint8* dict, uintxx size)
 		return;
 	}
 	PRVT->used = 1;
+}
+
+/* internal hooks for zstrm.c (hidden visibility) */
+void
+jdb_inflator_set_checks(TInflator* state, int which)
+{
+	PRVT->checks = which;
+}
+
+int
+jdb_inflator_get_checks(TInflator* state, uint32* crc, uint32* adler)
+{
+	uint32_t* h = (uint32_t*) (PRVT->pinned + 208);
+
+	if (jdb_copy_async(h, PRVT->dchecks, 8, PRVT->stream) != JDB_OK ||
+	    jdb_stream_sync(PRVT->stream) != JDB_OK) {
+		return -1;
+	}
+	*crc = h[0];
+	*adler = h[1];
+	return 0;
 }
 
 /* usage rules of the reference, src/inflator.c:729-762 */
@@ -332,6 +368,14 @@ inflator_inflate(TInflator* state, uint32 final)
 		PRVT->inqoff += (size_t) res->consumed;
 		PRVT->inqlen -= (size_t) res->consumed;
 		if (res->produced) {
+			if (PRVT->checks) {
+				if (jdb_dbuf_reserve(&PRVT->ckwork, jdb_checksum_workspace_bytes()) != 0 ||
+				    jdb_checksum(dst, (size_t) res->produced, PRVT->checks, PRVT->dchecks, PRVT->dchecks + 1,
+				                 PRVT->ckwork.ptr, PRVT->stream) != JDB_OK) {
+					poison(PRVT, INFLT_EOOM);
+					return INFLT_ERROR;
+				}
+			}
 			if (!tgt_on_device) {
 				if (jdb_copy_async(PBLC->target, dst, (size_t) res->produced, PRVT->stream) != JDB_OK ||
 				    jdb_stream_sync(PRVT->stream) != JDB_OK) {
