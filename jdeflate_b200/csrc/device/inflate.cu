@@ -189,10 +189,10 @@ build_table(WarpMem* m, uint32_t* table, int n, int kind, int lenoff)
 			if (i < 256) e = ENTRY(i, T_LIT, 0, 0);
 			else if (i == 256) e = ENTRY(0, T_EOB, 0, 0);
 			else if (i <= 285) e = ENTRY(c_len_base[i - 257], T_BASE, c_len_extra[i - 257], 0);
-			else continue;                  /* 286/287: never valid */
+			else e = ENTRY(0, T_BASE, 0, 0);   /* 286/287: reserved, base 0 marks them invalid */
 		} else if (kind == KIND_DIST) {
-			if (i > 29) continue;            /* 30/31: never valid */
-			e = ENTRY(c_dist_base[i], T_BASE, c_dist_extra[i], 0);
+			/* 30/31: reserved, base 0 marks them invalid */
+			e = i > 29 ? ENTRY(0, T_BASE, 0, 0) : ENTRY(c_dist_base[i], T_BASE, c_dist_extra[i], 0);
 		} else {
 			e = ENTRY(i, T_LIT, 0, 0);
 		}
@@ -569,6 +569,7 @@ inflate_stream(WarpMem* m, Stream& s)
 						}
 						bits_take(b, nb);
 						if (type == T_EOB) { ev = 1; break; }
+						if ((e >> 16) == 0) { ev = 4 + E_BADCODE; break; }     /* reserved symbol 286/287 */
 						/* length + distance */
 						uint32_t xb = (e >> 4) & 15u;
 						if (!fast && !bits_need(b, xb)) { b = save; ev = 2; break; }
@@ -588,6 +589,7 @@ inflate_stream(WarpMem* m, Stream& s)
 							else ev = 4 + E_BADCODE;
 							break;
 						}
+						if ((d >> 16) == 0) { ev = 4 + E_BADCODE; break; }     /* reserved symbol 30/31 */
 						bits_take(b, nb);
 						xb = (d >> 4) & 15u;
 						if (!fast && !bits_need(b, xb)) { b = save; ev = 2; break; }

@@ -11,8 +11,9 @@ from pathlib import Path
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
-if str(ROOT) not in sys.path:
-    sys.path.insert(0, str(ROOT))
+for _p in (str(ROOT), str(ROOT / "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 
 
 def pytest_configure(config):
@@ -51,3 +52,37 @@ def ref():
     if not p.exists():
         pytest.skip("oracle/_ref/libjdeflate_ref.so not built")
     return api.JDeflateLib(p)
+
+
+@pytest.fixture(scope="session")
+def emu():
+    """TEST INFRASTRUCTURE: the same kernel + host sources compiled for the CPU SIMT
+    emulator (tests/simt).  Lets `-m "not gpu"` exercise kernel and host logic through
+    the very same C ABI; it is never shipped and never used by the product."""
+    from jdeflate_b200 import api
+    from jdeflate_b200.build import build_emu
+    return api.JDeflateLib(build_emu())
+
+
+@pytest.fixture(scope="session", params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def lib(request):
+    """Library under test: the SIMT-emulator build on CPU, the product build on a B200."""
+    return request.getfixturevalue("emu" if request.param == "emu" else "jd")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from support import Oracle
+    return Oracle()
+
+
+@pytest.fixture(scope="session")
+def corpus():
+    from support import Corpus
+    return Corpus()
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import json
+    return json.loads((ROOT / "tests" / "golden" / "golden.json").read_text())

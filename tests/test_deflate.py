@@ -1,0 +1,145 @@
+"""Raw DEFLATE encode parity (reference deflator_deflate, src/deflator.c:690-786).
+
+Byte-identical output is not the goal of a chunk-parallel encoder; parity is:
+every stream decodes bit-exactly through the reference's decoder (oracle restatement, and the
+compiled reference when present) AND through zlib; the compressed size stays within 3 % of the
+reference encoder at the same level (oracle.deflate is byte-identical to the reference, see
+test_oracle.py); status codes and the streaming contract match."""
+import zlib
+
+import pytest
+
+from jdeflate_b200 import api
+from support import KIND_NAMES
+
+RATIO_TOLERANCE = 1.03      # BASELINE.json north_star: within 3 percent of jdeflate at the same level
+
+
+def check_stream(oracle, z, d):
+    assert zlib.decompress(z, -15) == d
+    st, err, out, used = oracle.inflate(z, len(d) + 1)
+    assert (st, err, used) == (api.OK, 0, len(z)) and out == d
+
+
+@pytest.mark.parametrize("kind", range(5))
+@pytest.mark.parametrize("level", [0, 1, 6, 9])
+def test_roundtrip_and_ratio(lib, oracle, corpus, kind, level):
+    for n in (1, 2, 3, 4, 5, 258, 4095, 16384, 16385, 70000, 300000):
+        d = corpus.fill(kind, n, offset=3 * n)
+        z = lib.deflate_bytes(d, level)
+        check_stream(oracle, z, d)
+        if n >= 70000:
+            ref = len(oracle.deflate(d, level))
+            assert len(z) <= RATIO_TOLERANCE * ref + 16, (KIND_NAMES[kind], n, level, len(z), ref)
+
+
+@pytest.mark.parametrize("level", [2, 3, 4, 5, 7, 8])
+def test_other_levels(lib, oracle, corpus, level):
+    d = corpus.fill(4, 120000, offset=11)
+    z = lib.deflate_bytes(d, level)
+    check_stream(oracle, z, d)
+    assert len(z) <= RATIO_TOLERANCE * len(oracle.deflate(d, level)) + 16
+
+
+def test_ratio_at_one_mib_mixed(lib, oracle, corpus):
+    """1 MiB straddling a TEXT -> BINARY segment boundary of the mixed corpus (BASELINE config 2 shape)."""
+    d = corpus.fill(5, 1 << 20, offset=(4 << 20) - (1 << 19))
+    z = lib.deflate_bytes(d, 6)
+    check_stream(oracle, z, d)
+    assert len(z) <= RATIO_TOLERANCE * len(oracle.deflate(d, 6))
+
+
+def test_empty_input(lib, oracle):
+    z = lib.deflate_bytes(b"", 6)
+    assert z == bytes([1, 0, 0, 0xff, 0xff])           # endstream(): src/deflator.c:609-654
+    check_stream(oracle, z, b"")
+
+
+def test_fixed_codes_flag(lib, oracle, corpus):
+    d = corpus.fill(0, 50000)
+    z = lib.deflate_bytes(d, 6, flags=api.DEFLT_FIXEDCODES)
+    check_stream(oracle, z, d)
+    # only fixed (BTYPE 01) or stored blocks: the first block header says so
+    assert (z[0] >> 1) & 3 == 1
+
+
+def test_incompressible_is_stored(lib, oracle, corpus):
+    d = corpus.fill(3, 100000)
+    z = lib.deflate_bytes(d, 6)
+    check_stream(oracle, z, d)
+    assert len(z) <= len(d) + 5 * (len(d) // 65535 + 2) + 5     # DESIGN.md deviation 6
+    assert len(z) < len(oracle.deflate(d, 6))
+
+
+def test_streaming_windows(lib, oracle, corpus):
+    """Any split of source pieces and target windows produces a valid stream
+    (reference resumability, src/deflator.c:96-109)."""
+    d = corpus.fill(1, 90000, offset=1)
+    whole = lib.deflate_bytes(d, 6)
+    for feed, window in ((1000, None), (None, 7), (4096, 100), (1, 65536)):
+        if feed == 1:
+            dd = d[:3000]
+            z = lib.deflate_bytes(dd, 6, feed=feed, window=window)
+            check_stream(oracle, z, dd)
+            continue
+        z = lib.deflate_bytes(d, 6, feed=feed, window=window)
+        check_stream(oracle, z, d)
+        assert z == whole          # input is batched internally: the split does not change the result
+
+
+def test_sync_flush_keeps_stream_valid(lib, oracle, corpus):
+    """DEFLT_FLUSH ends in the byte aligned marker 00 00 FF FF and the instance goes on
+    (src/deflator.c:763-768); the concatenation is one valid stream."""
+    a, b = corpus.fill(0, 40000), corpus.fill(0, 30000, offset=40000)
+    de = lib.deflator(6)
+    try:
+        za = de.run(a, flush=api.DEFLT_FLUSH)
+        assert za[-4:] == b"\x00\x00\xff\xff" and de.state != api.POISON
+        dz = zlib.decompressobj(-15)
+        assert dz.decompress(za) == a and not dz.eof
+        zb = de.run(b, flush=api.DEFLT_END)
+        assert de.state == api.POISON
+    finally:
+        de.close()
+    check_stream(oracle, za + zb, a + b)
+
+
+def test_status_codes_and_misuse(lib, corpus):
+    d = corpus.fill(0, 5000)
+    buf = bytearray(64)
+    de = lib.deflator(6)
+    try:
+        de.setsrc(d, len(d))
+        de.settgt(buf, len(buf))
+        assert de.deflate(api.DEFLT_NOFLUSH) == api.SRCEXHSTD
+        # again without new input and without a flush: src/deflator.c:663-688
+        assert de.deflate(api.DEFLT_NOFLUSH) == api.ERROR and de.error == api.DEFLT_EINCORRECTUSE
+        assert de.state == api.POISON
+        de.reset()
+        de.setsrc(d, len(d))
+        de.settgt(buf, len(buf))
+        assert de.deflate(api.DEFLT_END) == api.TGTEXHSTD and de.tgtend() == len(buf)
+        assert de.deflate(api.DEFLT_END) == api.ERROR and de.error == api.DEFLT_EINCORRECTUSE
+        de.reset()
+        # END is latched and cannot be downgraded: src/deflator.c:696-699
+        de.setsrc(d, len(d))
+        big = bytearray(8192)
+        de.settgt(big, len(big))
+        assert de.deflate(api.DEFLT_END) == api.OK
+        assert de.deflate(api.DEFLT_NOFLUSH) == api.ERROR and de.error == 0      # after the end: ERROR, error untouched
+    finally:
+        de.close()
+    assert not lib.lib.deflator_create(0, 10, None)
+    assert not lib.lib.deflator_create(0, -1, None)
+
+
+def test_reset_reuses_instance(lib, oracle, corpus):
+    de = lib.deflator(9)
+    try:
+        for k in (0, 2, 4):
+            d = corpus.fill(k, 20000, offset=k)
+            z = de.run(d)
+            check_stream(oracle, z, d)
+            de.reset()
+    finally:
+        de.close()

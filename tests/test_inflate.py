@@ -1,0 +1,114 @@
+"""Raw DEFLATE decode parity (reference inflator_inflate, src/inflator.c:764-903).
+Oracle: oracle/jd_oracle.c (pinned in test_oracle.py) and zlib; decoded bytes bit exact,
+status / error codes equal, input accounting exact."""
+import base64
+import random
+import zlib
+
+import pytest
+
+from jdeflate_b200 import api
+from support import KIND_NAMES, zlib_raw
+from test_oracle import RFC_DEVIATIONS
+
+
+def test_known_answer_streams(lib, golden):
+    for k in golden["inflate_kat"]:
+        s = base64.b64decode(k["stream"])
+        if not s:
+            continue
+        st, err, out, used = lib.inflate_bytes(s, k["cap"], final=bool(k["final"]))
+        want = RFC_DEVIATIONS.get(k["name"], (k["status"], k["error"]))
+        assert (st, err) == want, k["name"]
+        if k["name"] in RFC_DEVIATIONS:
+            continue
+        assert len(out) == k["out_len"] and zlib.crc32(out) == k["out_crc"], k["name"]
+        if st == api.OK:
+            assert used == k["exact_consumed"], k["name"]
+
+
+@pytest.mark.parametrize("kind", range(5))
+def test_third_party_and_reference_streams(lib, oracle, corpus, kind):
+    for n in (1, 100, 4096, 70000, 200000):
+        d = corpus.fill(kind, n, offset=17 * n)
+        streams = [zlib_raw(d, lvl) for lvl in (1, 6, 9)] + [oracle.deflate(d, lvl) for lvl in (0, 1, 6)]
+        for z in streams:
+            st, err, out, used = lib.inflate_bytes(z + b"\x55\xaa", n + 1)
+            want = oracle.inflate(z + b"\x55\xaa", n + 1)
+            assert (st, err, used) == (want[0], want[1], want[3]) == (api.OK, 0, len(z)), (KIND_NAMES[kind], n)
+            assert out == d
+
+
+def test_streaming_small_windows(lib, corpus):
+    """Resumability: any split of source and target windows gives the same bytes
+    (reference substate machinery, src/inflator.c:105-114)."""
+    d = corpus.fill(4, 50000, offset=5)
+    z = zlib_raw(d, 6)
+    for feed, window in ((1, 50001), (7, 13), (len(z), 1), (1000, 300), (33, 40000)):
+        st, err, out, used = lib.inflate_bytes(z, len(d), window=window, feed=feed)
+        assert (st, err) == (api.OK, 0), (feed, window)
+        assert out == d and used == len(z)
+
+
+def test_truncation_and_final_flag(lib, corpus):
+    d = corpus.fill(0, 30000)
+    z = zlib_raw(d, 6)
+    half = z[: len(z) // 2]
+    st, err, out, _ = lib.inflate_bytes(half, len(d), final=False)
+    assert (st, err) == (api.SRCEXHSTD, 0) and d.startswith(out) and len(out) > 0
+    st, err, out, _ = lib.inflate_bytes(half, len(d), final=True)
+    assert (st, err) == (api.ERROR, api.INFLT_EINPUTEND)
+    st, err, out, _ = lib.inflate_bytes(z, 1000)
+    assert st == api.TGTEXHSTD and out == d[:1000]
+
+
+def test_corrupted_streams_match_oracle(lib, oracle, corpus):
+    rnd = random.Random(99)
+    d = corpus.fill(4, 5000, offset=3)
+    z = zlib_raw(d, 6)
+    for _ in range(120):
+        m = bytearray(z)
+        for _ in range(rnd.randint(1, 3)):
+            m[rnd.randrange(len(m))] ^= 1 << rnd.randrange(8)
+        want = oracle.inflate(bytes(m), 6000)
+        got = lib.inflate_bytes(bytes(m), 6000)
+        assert (got[0], got[1]) == (want[0], want[1])
+        if want[0] == api.OK:
+            assert got[2] == want[2] and got[3] == want[3]
+        else:
+            assert got[2] == want[2][: len(got[2])] or want[2] == got[2][: len(want[2])]
+
+
+def test_sticky_error_and_misuse(lib, corpus):
+    s = lib.inflator()
+    try:
+        bad = bytes([0x07, 0, 0])                      # BFINAL=1, BTYPE=3
+        buf = bytearray(16)
+        s.setsrc(bad, len(bad))
+        s.settgt(buf, len(buf))
+        assert s.inflate(1) == api.ERROR and s.error == api.INFLT_EBADBLOCK and s.state == api.POISON
+        assert s.inflate(1) == api.ERROR and s.error == api.INFLT_EBADBLOCK
+        s.reset()
+        assert s.state == 0 and s.error == 0
+        z = zlib_raw(b"hello world, hello world", 6)
+        s.setsrc(z, len(z))
+        s.settgt(buf, 4)
+        assert s.inflate(1) == api.TGTEXHSTD
+        # asking again without a fresh target window is a usage error (src/inflator.c:729-762)
+        assert s.inflate(1) == api.ERROR and s.error == api.INFLT_EINCORRECTUSE
+    finally:
+        s.close()
+
+
+def test_preset_dictionary(lib, corpus):
+    dct = corpus.fill(0, 20000, offset=7)
+    d = dct[5000:9000] + corpus.fill(0, 3000, offset=999999)
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, zdict=dct)
+    z = co.compress(d) + co.flush()
+    s = lib.inflator()
+    try:
+        s.setdctnr(dct)
+        st, err, out, used = s.run(z, len(d))
+        assert (st, err, out, used) == (api.OK, 0, d, len(z))
+    finally:
+        s.close()
