@@ -1,0 +1,492 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native jdeflate codec.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mib M] [--level L]
+
+Metric (BASELINE.json): level-6 deflate GB/s of uncompressed bytes (GB = 1e9 B); the inflate
+figure of the same run rides in the "inflate" object of the JSON line.
+
+Workload at N = 1: BASELINE.json configs[1] -- gzip level 6 of 1 GiB of the mixed synthetic
+corpus (4 MiB segments cycling TEXT / BINARY / INCOMPRESSIBLE).  One step = one pass of the hot
+path over that 1 GiB.  At N > 1 every rank compresses its own 1 GiB slice of the corpus (weak
+scaling); the only collective is one all_gather of the per-rank {compressed bytes, crc32, length}
+that fixes the output offsets and the whole-stream CRC.
+
+  value      device-resident: input already in HBM, output to HBM, through the C ABI
+             (deflator_* on device pointers + the gzip CRC-32 of the input)
+  e2e        the same work through the reference-facing zstrm API with HOST buffers: pinned input,
+             zstrm_deflate(8 MiB pieces) -> target callback; every byte crosses PCIe inside the
+             timed region
+  roofline   the dominant kernel, timed live with CUDA events on its own stream (jdb200_profile)
+  cpu_baseline  the compiled reference (oracle/_ref) on the host cores, bounded sample
+  --impl reference   only the CPU reference arm, same metric / config
+
+Nothing here reads /root/reference at run time.  oracle/ is used only by the cpu_baseline and
+--impl reference legs (as the thing timed there) -- never on the product path.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import zlib
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+MIB = 1 << 20
+SEG = 4 * MIB                      # corpus segment (tools/corpus.c)
+MIXED = 5
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------
+
+def corpus_lib():
+    from support import Corpus
+    return Corpus()
+
+
+def fill_parallel(corpus, kind, addr, n, offset, threads=None):
+    """Generate [offset, offset+n) of a corpus straight into memory at `addr` (segments in parallel)."""
+    threads = threads or min(32, os.cpu_count() or 1)
+    jobs = []
+    pos = 0
+    while pos < n:
+        k = min(n - pos, SEG - ((offset + pos) % SEG))
+        jobs.append((pos, k))
+        pos += k
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(lambda j: corpus.fill_into(kind, addr + j[0], j[1], offset + j[0]), jobs))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+    return 7700.0 * 0.84, "fallback (B200_PROFILING.md: ~84 % of 7.7 TB/s nominal)"
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm (compiled reference on the host cores)
+# ---------------------------------------------------------------------------------------------
+
+def cpu_reference(corpus, op, level, sample_bytes, threads, offset=0):
+    """Times oracle/_ref/libjdeflate_ref.so (kind "reference") or, where it is absent, the oracle
+    port through the same driver.  Returns (GB/s, seconds, compressed bytes, kind)."""
+    base = C.CDLL(str(ROOT / "oracle" / "_ref" / "libjd_cpubase.so"))
+    base.jdcb_run.restype = C.c_int
+    base.jdcb_run.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int,
+                              C.POINTER(C.c_double), C.POINTER(C.c_size_t)]
+    ref = ROOT / "oracle" / "_ref" / "libjdeflate_ref.so"
+    if not ref.exists():
+        raise RuntimeError("oracle/_ref/libjdeflate_ref.so missing (build it in the build container: make -C oracle)")
+    buf = C.create_string_buffer(sample_bytes)
+    fill_parallel(corpus, MIXED, C.addressof(buf), sample_bytes, offset)
+    secs, comp = C.c_double(), C.c_size_t()
+    rc = base.jdcb_run(str(ref).encode(), op, level, buf, sample_bytes, threads, C.byref(secs), C.byref(comp))
+    if rc != 0:
+        raise RuntimeError(f"jdcb_run rc={rc}")
+    return sample_bytes / secs.value / 1e9, secs.value, comp.value, "reference"
+
+
+def cpu_sample_size(cores, total):
+    # ~12 MiB of the mixed corpus per core (whole TEXT/BINARY/INCOMP cycles), capped by the workload
+    n = 12 * MIB * max(1, cores)
+    n = max(12 * MIB, min(n, total))
+    return n - n % (12 * MIB) if n >= 12 * MIB else n
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    corpus = corpus_lib()
+    cores = os.cpu_count() or 1
+    total = args.mib * MIB
+    sample = cpu_sample_size(cores, total)
+    times = []
+    comp = 0
+    for i in range(args.warmup + args.steps):
+        gbs, secs, comp, kind = cpu_reference(corpus, 0, args.level, sample, cores)
+        if i >= args.warmup:
+            times.append(secs)
+    ms = 1e3 * sum(times) / len(times)
+    value = sample / (ms / 1e3) / 1e9
+    inf_gbs, _, _, _ = cpu_reference(corpus, 1, args.level, sample, cores)
+    line = {
+        "impl": "reference", "metric": "deflate_level%d_GBps_uncompressed" % args.level, "value": round(value, 4),
+        "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, extra={"note": "CPU reference: each step is a bounded sample of the workload"}),
+        "cpu_baseline": {"value": round(value, 4), "unit": "GB/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample // MIB} MiB of the mixed corpus, one reference TDeflator per core on contiguous slices"},
+        "e2e": {"value": round(value, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "inflate": {"value": round(inf_gbs, 4), "unit": "GB/s", "note": "reference TInflator per core on its own L%d slices" % args.level},
+        "ratio": round(sample / comp, 4), "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, extra=None):
+    c = {"workload": "gzip level %d of %d MiB mixed synthetic corpus (TEXT/BINARY/INCOMPRESSIBLE, 4 MiB segments) per GPU "
+                     "[BASELINE configs[1]]" % (args.level, args.mib),
+         "level": args.level, "bytes_per_gpu": args.mib * MIB, "container": "gzip",
+         "cache": "every step streams %d MiB of input (> the 126 MB L2) from HBM; no explicit flush" % args.mib}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mib", type=int, default=1024, help="uncompressed MiB per GPU per step")
+    ap.add_argument("--level", type=int, default=6)
+    ap.add_argument("--records", type=int, default=8192, help="distinct zlib JSON records of the inflate leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-inflate", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        log("note: the timing rules ask for >= 3 warm-up steps")
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    from jdeflate_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    jd = api.load()
+    assert jd.lib.jdb200_set_device(local) == 0, jd.lib.jdb200_last_error()
+    corpus = corpus_lib()
+    n = args.mib * MIB
+    cap = n + n // 8 + 65536
+
+    # ---- workload: this rank's slice of the mixed corpus, generated into pinned host memory ----
+    t0 = time.time()
+    host_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    fill_parallel(corpus, MIXED, host_in.data_ptr(), n, offset=rank * n)
+    dev_in = host_in.cuda(non_blocking=False)
+    dev_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    log(f"[rank {rank}] corpus ready in {time.time() - t0:.1f}s")
+
+    d = jd.deflator(args.level)
+    state = {}
+
+    def step_device():
+        d.reset()
+        d.setsrc(dev_in.data_ptr(), n)
+        d.settgt(dev_out.data_ptr(), cap)
+        r = d.deflate(api.DEFLT_END)
+        assert r == api.OK, (r, d.error, jd.lib.jdb200_last_error())
+        crc = jd.lib.zstrm_crc32update(0xFFFFFFFF, dev_in.data_ptr(), n) ^ 0xFFFFFFFF      # gzip trailer
+        state["produced"], state["crc"] = d.tgtend(), crc
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+
+    # ---- timed region: device-resident ----------------------------------------------------------
+    sampler = ClockSampler(local)
+    jd.profile(True)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    if dist is not None:
+        # the one collective of the path: per rank {compressed bytes, crc, length} -> offsets + stream CRC
+        mine = torch.tensor([state["produced"], state["crc"], n], dtype=torch.int64, device="cuda")
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    prof = jd.profile_read()
+    jd.profile(False)
+    ms_step = ms_total / args.steps
+    value = world * n / (ms_step / 1e3) / 1e9
+    produced = state["produced"]
+    launches = sum(v[0] for v in prof.values())
+
+    # correctness of what was timed (not in the timed region): zlib decodes it back, CRC matches
+    comp = dev_out[:produced].cpu().numpy().tobytes()
+    check_n = min(n, 64 * MIB)
+    dz = zlib.decompressobj(-15)
+    back = dz.decompress(comp, check_n)
+    assert back == host_in[:check_n].numpy().tobytes(), "decoded bytes differ from the input"
+    assert state["crc"] == zlib.crc32(host_in.numpy()), "CRC-32 mismatch"
+    del comp, back
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else ("none", (0, 0.0))
+    dom_name, (dom_launches, dom_ms) = dom
+    deflate_kernels = {k: v for k, v in prof.items() if not k.startswith("ck_")}
+    # one launch of a deflate-pipeline kernel covers one batch: algorithmic bytes = N (read) + C (written)
+    nbatches = max(1, prof.get("lz_kernel", (args.steps,))[0])
+    alg_bytes_per_launch = (n + produced) * args.steps / nbatches
+    achieved = alg_bytes_per_launch / (dom_ms / max(dom_launches, 1) / 1e3) / 1e9 if dom_ms else 0.0
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg_bytes_per_launch),
+                "avg_launch_ms": round(dom_ms / max(dom_launches, 1), 4),
+                "kernel_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in sorted(prof.items())},
+                "kernel_share_of_step": {k: round(v[1] / args.steps / ms_step, 4) for k, v in sorted(prof.items())}}
+    traffic_file = ROOT / "profiles" / "traffic.json"
+    if traffic_file.exists():
+        try:
+            roofline["traffic"] = json.loads(traffic_file.read_text()).get(dom_name)
+        except Exception:
+            pass
+
+    # ---- e2e: zstrm API, host buffers -----------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        out_base = host_out.data_ptr()
+        pos = {"p": 0}
+
+        def sink(buf, size, user):
+            C.memmove(out_base + pos["p"], buf, size)
+            pos["p"] += size
+            return size
+        cb = api.OFN(sink)
+        piece = 8 * MIB
+
+        def step_host():
+            z = jd.lib.zstrm_create(api.ZSTRM_DEFLATE | api.ZSTRM_GZIP, args.level, None)
+            assert z
+            pos["p"] = 0
+            jd.lib.zstrm_settargetfn(z, cb, None)
+            base = host_in.data_ptr()
+            for off in range(0, n, piece):
+                k = min(piece, n - off)
+                got = jd.lib.zstrm_deflate(z, base + off, k)
+                assert got == k, (got, z.contents.error)
+            jd.lib.zstrm_flush(z, 1)
+            assert z.contents.error == 0 and z.contents.state == 4
+            crc = z.contents.crc
+            jd.lib.zstrm_destroy(z)
+            return crc
+
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            crc = step_host()
+        barrier()
+        secs = (time.perf_counter() - t0) / e2e_steps
+        if dist is not None:
+            t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t.item())
+        gz = host_out[: pos["p"]].numpy().tobytes()
+        assert crc == zlib.crc32(host_in.numpy())
+        assert gz[-8:-4] == crc.to_bytes(4, "little") and gz[-4:] == (n & 0xFFFFFFFF).to_bytes(4, "little")
+        head = zlib.decompressobj(31).decompress(gz, 8 * MIB)
+        assert head == host_in[: len(head)].numpy().tobytes(), "e2e: decoded bytes differ from the input"
+        e2e = {"value": round(world * n / secs / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": n,
+               "d2h_bytes_per_step": pos["p"], "ms_per_step": round(secs * 1e3, 2), "steps": e2e_steps,
+               "api": "zstrm_create(DEFLATE|GZIP) / zstrm_deflate(8 MiB pieces from pinned host memory) / target callback / zstrm_flush(1)"}
+        del gz
+
+    # ---- inflate leg: batched zlib JSON records (BASELINE configs[2], scaled) ----------------------------
+    inflate = None
+    if not args.no_inflate:
+        inflate = bench_inflate(jd, corpus, args, torch, np, barrier, peak)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        sample = cpu_sample_size(cores, n)
+        try:
+            gbs, secs, csz, kind = cpu_reference(corpus, 0, args.level, sample, cores)
+            one = min(sample, 24 * MIB)
+            gbs1, secs1, _, _ = cpu_reference(corpus, 0, args.level, one, 1)
+            igbs, _, _, _ = cpu_reference(corpus, 1, args.level, sample, cores)
+            cpu = {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": kind,
+                   "sample": f"{sample // MIB} MiB of the same mixed corpus, one reference TDeflator per core on contiguous "
+                             f"slices ({secs:.1f} s wall)",
+                   "single_thread": {"value": round(gbs1, 4), "sample": f"{one // MIB} MiB"},
+                   "inflate": {"value": round(igbs, 4), "unit": "GB/s", "cores": cores},
+                   "ratio": round(sample / csz, 4)}
+        except Exception as ex:           # the baseline is reported, never required
+            cpu = {"value": None, "unit": "GB/s", "cores": cores, "kind": "reference", "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        line = {
+            "metric": "deflate_level%d_GBps_uncompressed" % args.level, "value": round(value, 3), "unit": "GB/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, {"chunk_kib": int(os.environ.get("JDB200_CHUNK_KIB", "256")),
+                                             "collective": "all_gather of 24 B per rank" if world > 1 else "none"}),
+            "ratio": round(n / produced, 4), "compressed_bytes_per_gpu": produced,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "inflate": inflate,
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    d.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_inflate(jd, corpus, args, torch, np, barrier, peak):
+    """Batched inflate of independent zlib JSON records (4-64 KiB, zlib level 6 = third-party
+    streams), one warp per record, device-resident buffers."""
+    from jdeflate_b200 import api
+    nd = args.records
+    t0 = time.time()
+    recs = [corpus.json_record(i) for i in range(nd)]
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        comp = list(ex.map(lambda r: zlib.compress(r, 6), recs))
+    tile = max(1, (1 << 30) // max(1, sum(map(len, recs))))          # ~1 GiB of output per step
+    count = nd * tile
+    perm = np.random.RandomState(1).permutation(count) % nd
+    clen = np.array([len(x) for x in comp], np.uint64)
+    rlen = np.array([len(x) for x in recs], np.uint64)
+    src_off = np.zeros(nd + 1, np.uint64)
+    src_off[1:] = np.cumsum(clen)
+    items = np.zeros((count, 4), np.uint64)
+    items[:, 0] = src_off[perm]
+    items[:, 2] = clen[perm]
+    items[:, 3] = rlen[perm]
+    items[1:, 1] = np.cumsum(rlen[perm])[:-1]
+    total_out = int(rlen[perm].sum())
+    total_in = int(clen[perm].sum())
+    src = torch.from_numpy(np.frombuffer(b"".join(comp), np.uint8).copy()).cuda()
+    out = torch.empty(total_out + 64, dtype=torch.uint8, device="cuda")
+    ditems = torch.from_numpy(items.view(np.int64)).cuda()
+    dres = torch.zeros((count, 4), dtype=torch.int64, device="cuda")
+    log(f"inflate leg: {nd} distinct records x{tile}, {total_out / 1e9:.2f} GB out, prep {time.time() - t0:.1f}s")
+
+    def step():
+        rc = jd.lib.jdb200_inflate_batch(src.data_ptr(), out.data_ptr(), ditems.data_ptr(), dres.data_ptr(), count, 1)
+        assert rc == 0, jd.lib.jdb200_last_error()
+
+    for _ in range(3):
+        step()
+    jd.profile(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    steps = max(3, args.steps)
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    prof = jd.profile_read()
+    jd.profile(False)
+    res = dres.cpu().numpy().view(np.uint32).reshape(count, 8)
+    assert int((res[:, 0] != 0).sum()) == 0 and int((res[:, 2] != 0).sum()) == 0, "inflate batch reported errors"
+    host = out.cpu().numpy()
+    for k in range(0, count, max(1, count // 64)):
+        o, ln = int(items[k, 1]), int(items[k, 3])
+        assert host[o:o + ln].tobytes() == recs[perm[k]], "inflate output mismatch"
+    kms = prof.get("inflate_batch_kernel", (steps, ms * steps))
+    kavg = kms[1] / max(kms[0], 1)
+    ach = (total_in + total_out) / (kavg / 1e3) / 1e9
+    return {"value": round(total_out / (ms / 1e3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(ms, 3),
+            "workload": f"batched inflate of {count} zlib level-6 JSON records (4-64 KiB, {nd} distinct) [BASELINE configs[2] scaled]",
+            "records": count, "bytes_out": total_out, "bytes_in": total_in,
+            "roofline": {"bound": "hbm", "kernel": "inflate_batch_kernel", "achieved": round(ach, 2), "peak": peak,
+                         "unit": "GB/s", "frac": round(ach / peak, 5), "avg_launch_ms": round(kavg, 4)}}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

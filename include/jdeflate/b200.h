@@ -67,6 +67,25 @@ int jdb200_set_device(int ordinal);
 JDEFLATE_API
 int jdb200_device_count(void);
 
+/*
+ * Launch accounting.  Every kernel launch of the library is counted per kernel;
+ * with profiling enabled each launch is also bracketed by CUDA events on the
+ * stream it runs on and the durations are summed (used by bench.py for the
+ * roofline of the dominant kernel).  jdb200_profile() resets the counters.
+ */
+typedef struct TJDB200KernelStat {
+	char   name[48];
+	uint64 launches;
+	double ms;
+} TJDB200KernelStat;
+
+JDEFLATE_API
+int jdb200_profile(int enable);
+
+/* fills up to `max` entries, returns how many; call after the work has finished */
+JDEFLATE_API
+int jdb200_profile_read(TJDB200KernelStat* stats, int max);
+
 /* last runtime error text of the calling thread ("" when none) */
 JDEFLATE_API
 const char* jdb200_last_error(void);

@@ -66,6 +66,23 @@ class JDVersion(C.Structure):
                 ("versionstring", C.c_char_p), ("builddate", C.c_char_p)]
 
 
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_uint64), ("ms", C.c_double)]
+
+
+class BatchItem(C.Structure):
+    """TJDB200Item: byte ranges relative to the batch base pointers."""
+    _fields_ = [("srcoffset", C.c_uint64), ("tgtoffset", C.c_uint64), ("srcsize", C.c_uint64), ("tgtsize", C.c_uint64)]
+
+
+class BatchResult(C.Structure):
+    """TJDB200Result."""
+    _fields_ = [("status", C.c_uint32), ("error", C.c_uint32), ("zerror", C.c_uint32), ("checksum", C.c_uint32),
+                ("srcused", C.c_uint64), ("tgtused", C.c_uint64)]
+
+
+JDB200_RAW, JDB200_ZLIB = 0, 1
+
 IFN = C.CFUNCTYPE(C.c_ssize_t, C.c_void_p, C.c_size_t, C.c_void_p)
 OFN = C.CFUNCTYPE(C.c_ssize_t, C.c_void_p, C.c_size_t, C.c_void_p)
 
@@ -142,6 +159,14 @@ class JDeflateLib:
         bind("zstrm_crc32combine", C.c_uint32, [C.c_uint32, C.c_uint32, C.c_size_t])
         bind("crc32_ncombine", C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint32])
 
+        # additive B200 entry points (include/jdeflate/b200.h); absent from the reference object
+        bind("jdb200_inflate_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int])
+        bind("jdb200_set_device", C.c_int, [C.c_int])
+        bind("jdb200_device_count", C.c_int, [])
+        bind("jdb200_last_error", C.c_char_p, [])
+        bind("jdb200_profile", C.c_int, [C.c_int])
+        bind("jdb200_profile_read", C.c_int, [C.POINTER(KernelStat), C.c_int])
+
     def has(self, name: str) -> bool:
         return hasattr(self.lib, name)
 
@@ -166,6 +191,40 @@ class JDeflateLib:
 
     def version(self) -> str:
         return self.lib.jdeflate_getversion().versionstring.decode()
+
+    # ---- additive B200 calls -------------------------------------------------
+    def profile(self, enable=True):
+        rc = self.lib.jdb200_profile(1 if enable else 0)
+        if rc:
+            raise RuntimeError(f"jdb200_profile rc={rc}")
+
+    def profile_read(self) -> dict:
+        """{kernel name: (launches, summed ms)}"""
+        arr = (KernelStat * 32)()
+        n = self.lib.jdb200_profile_read(arr, 32)
+        return {arr[i].name.decode(): (int(arr[i].launches), float(arr[i].ms)) for i in range(n)}
+
+    def inflate_batch(self, source, target, items, results, count, fmt=JDB200_RAW) -> int:
+        """All four arguments are addresses (host or device); see include/jdeflate/b200.h."""
+        return self.lib.jdb200_inflate_batch(_addr(source), _addr(target), _addr(items), _addr(results), count, fmt)
+
+    def inflate_batch_bytes(self, streams, sizes, fmt=JDB200_RAW):
+        """Host convenience: decode a list of byte strings; returns (outputs, results)."""
+        n = len(streams)
+        items = (BatchItem * n)()
+        so = to = 0
+        for i, (z, cap) in enumerate(zip(streams, sizes)):
+            items[i] = BatchItem(so, to, len(z), cap)
+            so += len(z)
+            to += cap
+        src = C.create_string_buffer(b"".join(streams), max(so, 1))
+        dst = C.create_string_buffer(max(to, 1))
+        res = (BatchResult * n)()
+        rc = self.lib.jdb200_inflate_batch(C.addressof(src), C.addressof(dst), C.addressof(items), C.addressof(res), n, fmt)
+        if rc:
+            raise RuntimeError(f"jdb200_inflate_batch rc={rc}: {self.lib.jdb200_last_error().decode()}")
+        outs = [dst.raw[items[i].tgtoffset: items[i].tgtoffset + res[i].tgtused] for i in range(n)]
+        return outs, list(res)
 
     # ---- object factories ----------------------------------------------
     def deflator(self, level=6, flags=0):

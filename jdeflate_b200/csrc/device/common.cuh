@@ -10,8 +10,15 @@
 	#include "simt_emu.h"
 #else
 	#include <cuda_runtime.h>
+	/* every kernel launch of the library goes through here: launches are counted
+	 * per kernel and, when profiling is on (jdb200_profile), bracketed by CUDA
+	 * events on the launching stream */
 	#define JDB_LAUNCH(kernel, grid, block, smem, stream, ...) \
-		kernel<<<(grid), (block), (smem), (cudaStream_t) (stream)>>>(__VA_ARGS__)
+		do { \
+			int jdb_prof_slot_ = jdb_prof_begin(#kernel, (stream)); \
+			kernel<<<(grid), (block), (smem), (cudaStream_t) (stream)>>>(__VA_ARGS__); \
+			jdb_prof_end(jdb_prof_slot_, (stream)); \
+		} while (0)
 	#define JDB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
@@ -22,6 +29,8 @@
 /* set by runtime.cu / runtime_emu.cpp */
 extern "C" int  jdb_rt_check_launch(const char* what);
 extern "C" void jdb_rt_set_error(const char* fmt, ...);
+extern "C" int  jdb_prof_begin(const char* kernel, jdb_stream s);
+extern "C" void jdb_prof_end(int slot, jdb_stream s);
 
 static __device__ __forceinline__ unsigned jdb_lane() { return threadIdx.x & 31u; }
 static __device__ __forceinline__ unsigned jdb_warp() { return threadIdx.x >> 5; }

@@ -34,6 +34,15 @@ int         jdb_rt_set_device(int ordinal);
 int         jdb_rt_get_device(void);
 int         jdb_rt_device_count(void);
 
+/* per-kernel launch counters and (optional) CUDA-event timing */
+typedef struct jdb_kernel_stat {
+	char     name[48];
+	uint64_t launches;
+	double   ms;          /* sum of event-timed durations (profiling on) */
+} jdb_kernel_stat;
+int  jdb_prof_enable(int on);                          /* resets the counters */
+int  jdb_prof_read(jdb_kernel_stat* out, int max);     /* caller has synchronised */
+
 void* jdb_dev_alloc(size_t bytes);
 void  jdb_dev_free(void* p);
 void* jdb_pinned_alloc(size_t bytes);

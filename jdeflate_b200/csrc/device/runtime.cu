@@ -181,3 +181,96 @@ extern "C" int jdb_stream_wait_event(jdb_stream s, jdb_event e)
 {
 	return check(cudaStreamWaitEvent((cudaStream_t) s, (cudaEvent_t) e, 0), "cudaStreamWaitEvent");
 }
+
+
+/* ---- launch accounting / profiling ------------------------------------------ */
+#include <pthread.h>
+
+#define PROF_KERNELS 24
+#define PROF_PENDING 4096
+
+static pthread_mutex_t g_prof_lock = PTHREAD_MUTEX_INITIALIZER;
+static int g_prof_on = 0;
+static int g_prof_n = 0;
+static jdb_kernel_stat g_prof[PROF_KERNELS];
+static struct { cudaEvent_t a, b; int kernel; int used; } g_pend[PROF_PENDING];
+static int g_pend_n = 0;
+
+static int prof_kernel_index(const char* name)
+{
+	/* `name` is the macro-stringified kernel expression: strip parentheses / template args */
+	char clean[48];
+	size_t k = 0;
+	for (const char* p = name; *p && k + 1 < sizeof(clean); p++) {
+		if (*p == '(' || *p == ')' || *p == ' ') continue;
+		clean[k++] = *p;
+	}
+	clean[k] = 0;
+	for (int i = 0; i < g_prof_n; i++)
+		if (strcmp(g_prof[i].name, clean) == 0) return i;
+	if (g_prof_n == PROF_KERNELS) return PROF_KERNELS - 1;
+	memset(&g_prof[g_prof_n], 0, sizeof(g_prof[0]));
+	strcpy(g_prof[g_prof_n].name, clean);
+	return g_prof_n++;
+}
+
+static void prof_resolve_locked(void)
+{
+	for (int i = 0; i < g_pend_n; i++) {
+		if (!g_pend[i].used) continue;
+		float ms = 0;
+		if (cudaEventSynchronize(g_pend[i].b) == cudaSuccess &&
+		    cudaEventElapsedTime(&ms, g_pend[i].a, g_pend[i].b) == cudaSuccess)
+			g_prof[g_pend[i].kernel].ms += ms;
+		g_pend[i].used = 0;
+	}
+	g_pend_n = 0;
+	cudaGetLastError();
+}
+
+extern "C" int jdb_prof_begin(const char* kernel, jdb_stream s)
+{
+	pthread_mutex_lock(&g_prof_lock);
+	int k = prof_kernel_index(kernel);
+	g_prof[k].launches++;
+	int slot = -1;
+	if (g_prof_on) {
+		if (g_pend_n == PROF_PENDING) prof_resolve_locked();
+		slot = g_pend_n++;
+		if (!g_pend[slot].a) {
+			cudaEventCreate(&g_pend[slot].a);
+			cudaEventCreate(&g_pend[slot].b);
+		}
+		g_pend[slot].kernel = k;
+		g_pend[slot].used = 1;
+		cudaEventRecord(g_pend[slot].a, (cudaStream_t) s);
+	}
+	pthread_mutex_unlock(&g_prof_lock);
+	return slot;
+}
+
+extern "C" void jdb_prof_end(int slot, jdb_stream s)
+{
+	if (slot < 0) return;
+	cudaEventRecord(g_pend[slot].b, (cudaStream_t) s);
+}
+
+extern "C" int jdb_prof_enable(int on)
+{
+	pthread_mutex_lock(&g_prof_lock);
+	prof_resolve_locked();
+	for (int i = 0; i < g_prof_n; i++) { g_prof[i].launches = 0; g_prof[i].ms = 0; }
+	g_prof_on = on != 0;
+	pthread_mutex_unlock(&g_prof_lock);
+	return JDB_OK;
+}
+
+extern "C" int jdb_prof_read(jdb_kernel_stat* out, int max)
+{
+	pthread_mutex_lock(&g_prof_lock);
+	prof_resolve_locked();
+	int n = g_prof_n < max ? g_prof_n : max;
+	for (int i = 0; i < n; i++) out[i] = g_prof[i];
+	pthread_mutex_unlock(&g_prof_lock);
+	return n;
+}

@@ -129,3 +129,20 @@ jdb200_last_error(void)
 {
 	return jdb_rt_last_error();
 }
+
+typedef char jdb_stat_layout_check[(sizeof(TJDB200KernelStat) == sizeof(jdb_kernel_stat)) ? 1 : -1];
+
+int
+jdb200_profile(int enable)
+{
+	if (jdb_rt_init() != JDB_OK) {
+		return JDB_ENODEV;
+	}
+	return jdb_prof_enable(enable);
+}
+
+int
+jdb200_profile_read(TJDB200KernelStat* stats, int max)
+{
+	return jdb_prof_read((jdb_kernel_stat*) stats, max);
+}

@@ -112,3 +112,32 @@ def test_preset_dictionary(lib, corpus):
         assert (st, err, out, used) == (api.OK, 0, d, len(z))
     finally:
         s.close()
+
+
+def test_batch_api(lib, oracle, corpus):
+    """jdb200_inflate_batch: per record results equal a fresh inflator fed the record with final = 1."""
+    recs = [corpus.json_record(i) for i in range(40)] + [b"", b"x"]
+    streams = [zlib.compress(r, 6) for r in recs]
+    outs, res = lib.inflate_batch_bytes(streams, [len(r) for r in recs], fmt=api.JDB200_ZLIB)
+    for r, z, o, q in zip(recs, streams, outs, res):
+        assert (q.status, q.error, q.zerror) == (api.OK, 0, 0)
+        assert o == r and q.srcused == len(z) and q.tgtused == len(r) and q.checksum == zlib.adler32(r)
+    # raw format, with damaged, truncated and over-long members in the same batch
+    raw = [zlib_raw(r, 6) for r in recs[:8]]
+    bad = bytearray(raw[3]); bad[len(bad) // 2] ^= 0x40
+    raw[3] = bytes(bad)
+    raw[5] = raw[5][: len(raw[5]) // 2]
+    caps = [len(r) for r in recs[:8]]
+    caps[6] = 100                                        # target too small
+    outs, res = lib.inflate_batch_bytes(raw, caps, fmt=api.JDB200_RAW)
+    for i in range(8):
+        want = oracle.inflate(raw[i], caps[i], final=True)
+        assert (res[i].status, res[i].error) == (want[0], want[1]), i
+        if want[0] == api.OK:
+            assert outs[i] == want[2]
+    assert res[5].status == api.ERROR and res[5].error == api.INFLT_EINPUTEND
+    assert res[6].status == api.TGTEXHSTD and outs[6] == recs[6][:100]
+    # checksum mismatch in a zlib member
+    z = bytearray(streams[0]); z[-1] ^= 1
+    _, res = lib.inflate_batch_bytes([bytes(z)], [len(recs[0])], fmt=api.JDB200_ZLIB)
+    assert res[0].status == api.OK and res[0].zerror == api.ZSTRM_ECHECKSUM
