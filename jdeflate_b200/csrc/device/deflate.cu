@@ -102,8 +102,16 @@ extern "C" int jdb_deflate_run(const uint8_t* in, uint64_t n, const jdb_deflate_
 		/* segment indexing is chunk relative (a chunk owns chunk_bytes/SEG slots) only
 		 * when the chunk size is a multiple of SEG, which plan() enforces, so the
 		 * global segment index k*SEG is the same thing */
-		uint32_t range = cfg->chain_range ? cfg->chain_range : cfg->chunk_bytes;
-		if (range > cfg->chunk_bytes || cfg->chunk_bytes % range) range = cfg->chunk_bytes;
+		/* positions per chain-building warp: a whole chunk when the batch has enough
+		 * chunks to fill the GPU (3 resident warps per SM, several waves), otherwise
+		 * sub-ranges that each replay 32 KiB of history first */
+		uint32_t range = cfg->chain_range;
+		if (range == 0) {
+			const uint64_t want = (uint64_t) jdb_rt_sm_count() * 3 * 4;
+			range = cfg->chunk_bytes;
+			while (range > 65536 && (range & 1) == 0 && (range / 2) % SEG == 0 && (n + range - 1) / range < want) range /= 2;
+		}
+		if (range > cfg->chunk_bytes || cfg->chunk_bytes % range || range % SEG) range = cfg->chunk_bytes;
 		r = jdb_lz_chain(in, n, cfg->chunk_bytes, range, prev, s);
 		if (r != JDB_OK) return r;
 		r = jdb_lz_parse(in, n, cfg->chunk_bytes, prev, cfg->good, cfg->nice, cfg->chain, cfg->lazy,

@@ -65,50 +65,93 @@ chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, u
 	if (chunk1 > n) chunk1 = n;
 	uint64_t r1 = r0 + range;
 	if (r1 > chunk1) r1 = chunk1;
-	uint64_t start = r0 >= chunk0 + WND ? r0 - WND : chunk0;   /* warm-up start */
+	const uint64_t start = r0 >= chunk0 + WND ? r0 - WND : chunk0;   /* warm-up start, multiple of SEG */
 
 	/* positions are handled relative to `start`; an entry holds the low 16
 	 * bits, "empty" is anything that decodes to a distance >= 32768 */
 	for (uint32_t i = lane; i < (1u << HASH_BITS); i += 32) head[i] = 0x8000u;
 	__syncwarp();
 
-	const uint64_t last_hashable = chunk1 >= 4 ? chunk1 - 4 : 0;   /* inclusive; needs chunk1 >= 4 */
-	for (uint64_t base = start; base < r1; base += 32) {
-		const uint32_t rel = (uint32_t) (base - start);
-		if (rel && (rel & (WND - 1)) == 0) {
+	/* Input is consumed in blocks of 128 positions: one coalesced 128-byte load
+	 * per block (lane i holds word i), prefetched two blocks ahead so the loop
+	 * never waits for HBM; every lane assembles its 4 bytes with two shuffles. */
+	const uint32_t* words = (const uint32_t*) (in + start);
+	const uint64_t nwords = (n - start + 3) / 4;                 /* words that start before `n` */
+	const uint32_t span = (uint32_t) (r1 - start);
+	const uint32_t nblocks = (span + 127) / 128;
+	const uint32_t hashable = chunk1 - start >= 4 ? (uint32_t) (chunk1 - start - 3) : 0;   /* rel < hashable */
+	const uint32_t emit0 = (uint32_t) (r0 - start);
+
+#define LOADW(blk) ((uint64_t) (blk) * 32 + lane < nwords ? __ldg(words + (uint64_t) (blk) * 32 + lane) : 0u)
+	uint32_t w0 = LOADW(0), w1 = LOADW(1), w2 = LOADW(2);
+	for (uint32_t blk = 0; blk < nblocks; blk++) {
+		const uint32_t w3 = LOADW(blk + 3);
+		const uint32_t rel0 = blk * 128;
+		if (rel0 && (rel0 & (WND - 1)) == 0) {
 			/* every 32768 positions retire entries that are out of the window
 			 * so 16-bit positions never alias (cf. slidehash) */
-			const uint32_t stale = (rel + 0x8000u) & 0xffffu;
+			const uint32_t stale = (rel0 + 0x8000u) & 0xffffu;
 			for (uint32_t i = lane; i < (1u << HASH_BITS); i += 32) {
-				uint32_t d = (rel - head[i]) & 0xffffu;
+				uint32_t d = (rel0 - head[i]) & 0xffffu;
 				if (d >= WND) head[i] = (uint16_t) stale;
 			}
 			__syncwarp();
 		}
-		const uint64_t p = base + lane;
-		const bool valid = chunk1 >= 4 && p <= last_hashable;
-		uint32_t h = 0xffffffffu - lane;                 /* unique per lane when invalid */
-		if (valid) {
-			const uint8_t* q = in + p;
-			uint32_t be = ((uint32_t) q[0] << 24) | ((uint32_t) q[1] << 16) | ((uint32_t) q[2] << 8) | q[3];
-			h = (be * HASH_MUL) >> (32 - HASH_BITS);
-		}
-		const unsigned same = __match_any_sync(JDB_FULL_MASK, h);
-		uint32_t dist = 0;
-		if (valid) {
-			const unsigned lower = same & ((1u << lane) - 1u);
-			if (lower) {
-				dist = lane - (31 - __clz(lower));
-			} else {
-				uint32_t d = ((rel + lane) - head[h]) & 0xffffu;
-				if (d < WND && d <= rel + lane) dist = d;
+		/* hashes of the four groups of 32 first (independent work, off the serial path) */
+		uint32_t hh[4];
+#pragma unroll
+		for (uint32_t j = 0; j < 4; j++) {
+			const uint32_t idx = 8 * j + (lane >> 2);
+			const uint32_t lo = __shfl_sync(JDB_FULL_MASK, w0, idx);
+			uint32_t hi = __shfl_sync(JDB_FULL_MASK, w0, (idx + 1) & 31);
+			if (j == 3) {
+				const uint32_t hn = __shfl_sync(JDB_FULL_MASK, w1, 0);
+				if (idx == 31) hi = hn;
 			}
+			const uint32_t le = __funnelshift_r(lo, hi, (lane & 3u) * 8u);
+			const uint32_t be = __byte_perm(le, 0, 0x0123);
+			hh[j] = (be * HASH_MUL) >> (32 - HASH_BITS);
 		}
-		__syncwarp();
-		if (valid && (same >> lane) == 1u) head[h] = (uint16_t) (rel + lane);   /* highest lane of its group */
-		if (p >= r0 && p < r1) prev[p] = (uint16_t) dist;
-		__syncwarp();
+		uint32_t dd[4];
+#pragma unroll
+		for (uint32_t j = 0; j < 4; j++) {
+			const uint32_t rel = rel0 + 32 * j + lane;
+			const bool valid = rel < hashable;
+			/* Two lanes with the same hash in one group of 32 are rare (runs, short
+			 * periods).  Fast path: everybody reads the old head, everybody stores its
+			 * own position, and a read-back tells whether any store lost, i.e. whether
+			 * duplicates exist; only then the exact (slow) match_any resolution runs. */
+			const uint32_t slot = valid ? hh[j] : 0;
+			const uint32_t old = head[slot];
+			__syncwarp();
+			if (valid) head[slot] = (uint16_t) rel;
+			__syncwarp();
+			const bool lost = valid && head[slot] != (uint16_t) rel;
+			uint32_t dist = 0;
+			if (valid) {
+				const uint32_t d = (rel - old) & 0xffffu;
+				if (d < WND && d <= rel) dist = d;
+			}
+			if (__ballot_sync(JDB_FULL_MASK, lost)) {
+				const unsigned same = __match_any_sync(JDB_FULL_MASK, valid ? hh[j] : 0xffffffffu - lane);
+				if (valid) {
+					const unsigned lower = same & ((1u << lane) - 1u);
+					if (lower) dist = lane - (31 - __clz(lower));
+				}
+				__syncwarp();
+				if (valid && (same >> lane) == 1u) head[slot] = (uint16_t) rel;   /* highest lane of its group */
+				__syncwarp();
+			}
+			dd[j] = dist;
+		}
+#pragma unroll
+		for (uint32_t j = 0; j < 4; j++) {
+			const uint32_t rel = rel0 + 32 * j + lane;
+			if (rel >= emit0 && rel < span) prev[start + rel] = (uint16_t) dd[j];
+		}
+		w0 = w1; w1 = w2; w2 = w3;
 	}
+#undef LOADW
 }
 
 /* ---------------------------------------------------------------------------
@@ -116,10 +159,22 @@ chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, u
  * ------------------------------------------------------------------------- */
 
 #define LZ_THREADS   1024
+#ifndef LZ_WALK_STEPS
+#define LZ_WALK_STEPS 4
+#endif
 #define PER_THREAD   (SEG / LZ_THREADS)            /* 16 */
 #define WALK_BLOCK   256u
 #define WALKERS      (SEG / WALK_BLOCK)            /* 64 */
 #define DATA_BYTES   (WND + SEG + 320)             /* history + segment + look-ahead/guard */
+
+#ifdef JDB_SIMT_EMU
+/* emulator-only instrumentation (tools/emu_lz_stats.py): loop iterations per
+ * thread and chain steps per position */
+extern "C" { uint32_t* jdb_emu_lz_iters = 0; uint8_t* jdb_emu_lz_steps = 0; uint64_t jdb_emu_lz_cnt[8] = {0}; }
+#define LZ_STAT(x) x
+#else
+#define LZ_STAT(x)
+#endif
 
 struct LzParams {
 	uint32_t good, nice, chain, lazy;
@@ -135,6 +190,7 @@ struct LzSmem {
 	uint32_t land[WALKERS];          /* where each walker left its block      */
 	uint32_t merge[WALKERS];
 	uint32_t warp_sum[LZ_THREADS / 32];
+	uint32_t next_pos;               /* work distribution of the match search */
 };
 
 static __device__ __forceinline__ uint32_t ilog2_u32(uint32_t v) { return 31 - __clz(v); }
@@ -177,57 +233,129 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 		for (uint32_t i = tid; i < nv; i += LZ_THREADS) dst[i] = __ldg(src + i);
 		for (uint32_t i = nv * 16 + tid; i < DATA_BYTES; i += LZ_THREADS)
 			S.data[i] = i < nbytes ? in[hist0 + i] : 0;
+		/* links are staged as absolute shared-memory positions (0xffff = none), so a
+		 * chain step is one load and one range check */
 		const uint32_t nlinks = hoff + seg_len;
 		const uint4* ps = (const uint4*) (prev + hist0);
-		uint4* pd = (uint4*) S.prev;
 		const uint32_t npv = nlinks / 8;
-		for (uint32_t i = tid; i < npv; i += LZ_THREADS) pd[i] = __ldg(ps + i);
-		for (uint32_t i = npv * 8 + tid; i < nlinks; i += LZ_THREADS) S.prev[i] = prev[hist0 + i];
+		for (uint32_t i = tid; i < npv; i += LZ_THREADS) {
+			const uint4 v = __ldg(ps + i);
+			const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+			uint32_t o[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const uint32_t i0 = i * 8 + 2 * u, i1 = i0 + 1;
+				const uint32_t d0 = w[u] & 0xffffu, d1 = w[u] >> 16;
+				const uint32_t l0 = (d0 && d0 <= i0) ? i0 - d0 : 0xffffu;
+				const uint32_t l1 = (d1 && d1 <= i1) ? i1 - d1 : 0xffffu;
+				o[u] = l0 | (l1 << 16);
+			}
+			((uint4*) S.prev)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+		}
+		for (uint32_t i = npv * 8 + tid; i < nlinks; i += LZ_THREADS) {
+			const uint32_t d = prev[hist0 + i];
+			S.prev[i] = (uint16_t) ((d && d <= i) ? i - d : 0xffffu);
+		}
+		if (tid == 0) S.next_pos = 0;
 		for (uint32_t i = tid; i < SEG / 32; i += LZ_THREADS) { S.spec[i] = 0; S.fix[i] = 0; }
 		for (uint32_t i = tid; i < NSYM; i += LZ_THREADS) S.hist[i] = 0;
 	}
 	__syncthreads();
 
-	/* ---- match search: thread t handles positions t, t+1024, ... ---- */
-	for (uint32_t k = 0; k < PER_THREAD; k++) {
-		const uint32_t p = tid + k * LZ_THREADS;
-		uint32_t result = 0;
-		if (p < seg_len) {
-			const uint32_t j = hoff + p;                                /* smem coordinate */
-			uint32_t maxlen = (uint32_t) (seg1 - (seg0 + p));          /* never past the segment */
-			if (maxlen > MAXLEN) maxlen = MAXLEN;
-			if (maxlen >= MINLEN) {
-				uint32_t best = MINLEN - 1, bestd = 0;
-				uint32_t cur = j, steps = prm.chain;
-				uint32_t d = S.prev[cur];
-				const uint32_t w0 = jdb_ld32u(S.data, j);
-				while (d != 0 && steps-- != 0) {
-					if (d > cur) break;
-					const uint32_t q = cur - d;
-					const uint32_t total = j - q;
-					if (total >= WND) break;
-					/* pre-filter on the byte that would extend the best match */
-					if (S.data[q + best] == S.data[j + best] && jdb_ld32u(S.data, q) == w0) {
-						uint32_t len = 4;
-						while (len < maxlen) {
-							uint32_t x = jdb_ld32u(S.data, j + len) ^ jdb_ld32u(S.data, q + len);
-							if (x) { len += (uint32_t) (__ffs((int) x) - 1) >> 3; break; }
-							len += 4;
-						}
-						if (len > maxlen) len = maxlen;
-						if (len > best) {
-							best = len;
-							bestd = total;
-							if (len >= prm.nice || len == maxlen) break;
+	/* ---- match search -------------------------------------------------------
+	 * Positions are handed out dynamically (one shared counter, warp-aggregated).
+	 * A lane is in one of three modes and the warp runs three phases per round:
+	 *   WALK     one chain step: next link, window / budget check, pre-filter on
+	 *            the byte that would extend the best match so far
+	 *   COMPARE  up to 16 more bytes of the candidate that passed the pre-filter
+	 *   FETCH    store the finished position, take the next one
+	 * WALK runs every round; COMPARE and FETCH only when enough lanes wait for
+	 * them (or nobody can walk), so the two rare, long phases execute with many
+	 * lanes active instead of diverging on every step. */
+	{
+		enum { M_FETCH = 0, M_WALK = 1, M_COMPARE = 2, M_DONE = 3 };
+		const uint32_t nice = prm.nice;
+		const uint32_t lane = tid & 31u;
+		uint32_t mode = M_FETCH;
+		uint32_t p = 0xffffffffu, j = 0, jmin = 0, maxlen = 0, best = 0, bestd = 0, cur = 0, steps = 0, cb = 0;
+		uint32_t cq = 0, clen = 0, dmax = 0;
+		for (;;) {
+			/* a few chain steps per round amortise the phase bookkeeping below; a lane
+			 * that leaves WALK mode sits out the remaining steps */
+#pragma unroll
+			for (int u = 0; u < LZ_WALK_STEPS; u++) {
+				if (mode == M_WALK) {
+					const uint32_t q = S.prev[cur];
+					LZ_STAT(if (jdb_emu_lz_steps) jdb_emu_lz_steps[seg0 + p]++;)
+					if (q - jmin >= dmax || steps == 0) mode = M_FETCH;          /* not in [jmin, j) */
+					else {
+						steps--;
+						cur = q;
+						if (S.data[q + best] == cb) { cq = q; clen = 0; mode = M_COMPARE; }
+					}
+				}
+			}
+			/* mode bits: FETCH 00, WALK 01, COMPARE 10, DONE 11 */
+			const unsigned bit0 = __ballot_sync(JDB_FULL_MASK, mode & 1u);
+			const unsigned bit1 = __ballot_sync(JDB_FULL_MASK, mode & 2u);
+			const unsigned walkers = bit0 & ~bit1, comparers = bit1 & ~bit0, fetchers = ~(bit0 | bit1);
+			if ((bit0 & bit1) == JDB_FULL_MASK) break;
+			if (comparers && (walkers == 0 || __popc(comparers) >= 8)) {
+				if (mode == M_COMPARE) {
+					uint32_t len = clen;
+					bool done = false;
+#pragma unroll
+					for (int u = 0; u < 4; u++) {
+						if (!done) {
+							if (len >= maxlen) done = true;
+							else {
+								const uint32_t x = jdb_ld32u(S.data, j + len) ^ jdb_ld32u(S.data, cq + len);
+								if (x) { len += (uint32_t) (__ffs((int) x) - 1) >> 3; done = true; }
+								else len += 4;
+							}
 						}
 					}
-					cur = q;
-					d = S.prev[cur];
+					if (!done && len >= maxlen) done = true;
+					if (done) {
+						if (len > maxlen) len = maxlen;
+						mode = M_WALK;
+						if (len > best) {
+							best = len;
+							bestd = j - cq;
+							cb = S.data[j + best];
+							if (len >= nice || len == maxlen) mode = M_FETCH;
+						}
+					} else {
+						clen = len;
+					}
 				}
-				if (best >= MINLEN) result = (best << 16) | bestd;
+			}
+			if (fetchers && (walkers == 0 || __popc(fetchers) >= 8)) {
+				uint32_t base = 0;
+				const uint32_t leader = (uint32_t) __ffs((int) fetchers) - 1;
+				if (lane == leader) base = atomicAdd(&S.next_pos, (uint32_t) __popc(fetchers));
+				base = __shfl_sync(JDB_FULL_MASK, base, leader);
+				if (fetchers & (1u << lane)) {
+					if (p != 0xffffffffu) S.m[p] = best >= MINLEN ? (best << 16) | bestd : 0;
+					p = base + (uint32_t) __popc(fetchers & ((1u << lane) - 1u));
+					if (p >= SEG) { mode = M_DONE; p = 0xffffffffu; }
+					else if (p >= seg_len || seg_len - p < MINLEN) {
+						/* nothing to find here; stay in FETCH */
+						S.m[p] = 0;
+						p = 0xffffffffu;
+					} else {
+						maxlen = seg_len - p;                     /* never past the segment */
+						if (maxlen > MAXLEN) maxlen = MAXLEN;
+						j = hoff + p;
+						jmin = j > WND - 1 ? j - (WND - 1) : 0;
+						dmax = j - jmin;
+						best = MINLEN - 1; bestd = 0; cur = j; steps = prm.chain;
+						cb = S.data[j + best];
+						mode = M_WALK;
+					}
+				}
 			}
 		}
-		if (p < SEG) S.m[p] = result;
 	}
 	__syncthreads();
 

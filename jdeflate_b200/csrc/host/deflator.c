@@ -26,7 +26,7 @@
 #define POISON 0xDEADBEEFu
 
 /* batch geometry (overridable through the environment for experiments) */
-#define DEFAULT_BATCH   ((size_t) 64 << 20)
+#define DEFAULT_BATCH   ((size_t) 256 << 20)
 #define DEFAULT_CHUNK   ((size_t) 256 << 10)
 #define DEFAULT_BLOCKSEGS 4
 
@@ -134,7 +134,7 @@ deflator_create(uintxx flags, intxx level, const TAllocator* allctr)
 	PRVT->cfg.chunk_bytes = (uint32_t) chunk;
 	PRVT->cfg.block_segs = (uint32_t) env_size("JDB200_BLOCK_SEGS", DEFAULT_BLOCKSEGS);
 	if (PRVT->cfg.block_segs > 16) PRVT->cfg.block_segs = 16;
-	PRVT->cfg.chain_range = chunk > (128u << 10) && (chunk % (128u << 10)) == 0 ? (128u << 10) : 0;
+	PRVT->cfg.chain_range = (uint32_t) env_size("JDB200_CHAIN_RANGE_KIB", 0) << 10;     /* 0: chosen per batch */
 	PRVT->cfg.fixedonly = (flags & DEFLT_FIXEDCODES) != 0;
 	PRVT->batchcap = env_size("JDB200_BATCH_MIB", DEFAULT_BATCH >> 20) << 20;
 	PRVT->batchcap = (PRVT->batchcap + chunk - 1) / chunk * chunk;

@@ -18,6 +18,7 @@ for kind in kinds:
     out = torch.empty(n + n // 8 + 65536, dtype=torch.uint8, device="cuda")
     for lvl in levels:
         best = 1e9
+        jd.profile(True)
         for it in range(4):
             d = jd.deflator(lvl)
             d.setsrc(src.data_ptr(), n)
@@ -28,6 +29,8 @@ for kind in kinds:
             best = min(best, dt)
             produced = d.tgtend(); consumed = d.srcend()
             d.close()
+        prof = jd.profile_read(); jd.profile(False)
+        print("   per call ms:", {k: round(v[1] / 4, 3) for k, v in prof.items()}, flush=True)
         comp = out[:produced].cpu().numpy().tobytes()
         ok = zlib.decompress(comp, -15) == host.tobytes()
         sample = host[: 8 << 20].tobytes()
