@@ -8,25 +8,32 @@
  * Two kernels:
  *
  *  chain_kernel   builds, for every input position, the distance to the
- *                 previous position with the same 4-byte hash -- exactly the
- *                 links the reference's insert-every-position policy produces
- *                 in mchain[] (the chain content does not depend on the parse,
- *                 only on the data).  One warp per range of a chunk, hash heads
- *                 in shared memory (2^15 x u16), 32 positions per step resolved
- *                 with __match_any_sync.  Hash: big-endian 4 bytes * 0x1e35a7bd
- *                 (gethead/gethash, src/deflator.c:1930-1947), top 15 bits.
+ *                 previous position with the same 4-byte hash -- the links the
+ *                 reference's insert-every-position policy produces in
+ *                 mchain[] (the chain content does not depend on the parse,
+ *                 only on the data).  Hash: big-endian 4 bytes * 0x1e35a7bd
+ *                 (gethead/gethash, src/deflator.c:1930-1947), top 14 bits
+ *                 (the reference keeps 16; measured cost of 14: +1.5 % chain
+ *                 steps, +0.04 % size).  The head-table update is a serial
+ *                 dependency, so throughput = tables resident per SM / step
+ *                 latency: a 32 KiB table (2^14 x u16) lets six CTAs share an
+ *                 SM.  A CTA is a producer warp (coalesced prefetched loads,
+ *                 hashing, link write-back) and a consumer warp (head table),
+ *                 32 positions per step, duplicates inside a step detected by
+ *                 a store / read-back and resolved with match_any over the
+ *                 lanes involved only.
  *
  *  lz_kernel      one CTA per 16 KiB segment.  The 32 KiB of history plus the
  *                 segment (bytes and chain links) are staged in shared memory;
- *                 every thread then walks the chains of its positions
- *                 (bounded by the level's max chain, early exit at `nice`,
- *                 the reference's strbgn[len]==pmatch[len] pre-filter) --
- *                 the search is position-parallel because on the compression
- *                 side the history is the input itself.  The lazy / greedy
- *                 selection (good length, the reference's offset-aware accept
- *                 rule src/deflator.c:2860-2879) is evaluated per position,
- *                 and the one truly serial step -- following the chosen tokens
- *                 from the segment start -- is done by 64 speculative walkers
+ *                 every position is searched (bounded by the level's max
+ *                 chain, early exit at `nice`, the reference's
+ *                 strbgn[len]==pmatch[len] pre-filter) -- the search is
+ *                 position-parallel because on the compression side the
+ *                 history is the input itself.  The lazy / greedy selection
+ *                 (good length, the reference's offset-aware accept rule
+ *                 src/deflator.c:2860-2879) is evaluated per position, and the
+ *                 one truly serial step -- following the chosen tokens from
+ *                 the segment start -- is done by 64 speculative walkers
  *                 whose paths are stitched exactly (paths re-converge within a
  *                 few tokens).  Tokens are compacted with a block scan and
  *                 written coalesced; symbol histograms are accumulated with
@@ -38,7 +45,7 @@
  */
 #include "deflate.cuh"
 
-#define HASH_BITS      15
+#define HASH_BITS      14
 #define HASH_MUL       0x1e35a7bdu
 
 /* ---------------------------------------------------------------------------
@@ -49,14 +56,121 @@
  * Work item r covers positions [r*range, (r+1)*range) of the batch; ranges
  * never straddle chunks (range divides the chunk size).  A range that does not
  * start a chunk first replays the preceding 32 KiB without emitting links.
+ *
+ * The head-table update is a serial dependency (group g+1 must see the heads
+ * group g stored), so one warp runs it with nothing else on its plate and a
+ * second warp feeds it: warp 0 ("producer") streams the input with coalesced,
+ * prefetched 128-byte loads, hashes 128 positions per round into a shared
+ * ring and writes the finished links of the round before last to HBM; warp 1
+ * ("consumer") turns hashes into links.  One __syncthreads per round.
  */
-__global__ void __launch_bounds__(32)
+#define CH_THREADS   64
+#define CH_BLOCK     128u                  /* positions per round */
+#define CH_DUMMY     (1u << HASH_BITS)     /* 32 private slots for positions that are not hashed */
+
+struct ChainSmem {
+	uint16_t head[(1u << HASH_BITS) + 32];
+	uint16_t hash[2][CH_BLOCK];
+	uint16_t dist[2][CH_BLOCK];
+};
+
+/* producer: hash block `blk` (lane i holds word i of the block, `wnext` word i of the
+ * next one); every lane assembles the 4 bytes of its position with two shuffles */
+static __device__ __forceinline__ void
+chain_hash_block(ChainSmem& S, uint32_t blk, uint32_t wcur, uint32_t wnext, uint32_t hashable, unsigned lane)
+{
+	const uint32_t rel0 = blk * CH_BLOCK;
+#pragma unroll
+	for (uint32_t j = 0; j < 4; j++) {
+		const uint32_t idx = 8 * j + (lane >> 2);
+		const uint32_t lo = __shfl_sync(JDB_FULL_MASK, wcur, idx);
+		uint32_t hi = __shfl_sync(JDB_FULL_MASK, wcur, (idx + 1) & 31);
+		if (j == 3) {
+			const uint32_t hn = __shfl_sync(JDB_FULL_MASK, wnext, 0);
+			if (idx == 31) hi = hn;
+		}
+		const uint32_t le = __funnelshift_r(lo, hi, (lane & 3u) * 8u);
+		const uint32_t be = __byte_perm(le, 0, 0x0123);
+		const uint32_t rel = rel0 + 32 * j + lane;
+		const uint32_t h = rel < hashable ? (be * HASH_MUL) >> (32 - HASH_BITS) : CH_DUMMY + lane;
+		S.hash[blk & 1][32 * j + lane] = (uint16_t) h;
+	}
+}
+
+/* producer: links of block `blk`, finished by the consumer in the previous round, to HBM */
+static __device__ __forceinline__ void
+chain_emit_block(ChainSmem& S, uint32_t blk, uint16_t* __restrict__ out, uint32_t emit0, uint32_t span, unsigned lane)
+{
+	const uint32_t rel0 = blk * CH_BLOCK;
+#pragma unroll
+	for (uint32_t j = 0; j < 4; j++) {
+		const uint32_t rel = rel0 + 32 * j + lane;
+		if (rel >= emit0 && rel < span) out[rel] = S.dist[blk & 1][32 * j + lane];
+	}
+}
+
+/* consumer: hashes of block `blk` -> links, head table update */
+static __device__ __forceinline__ void
+chain_link_block(ChainSmem& S, uint32_t blk, unsigned lane)
+{
+	const uint32_t rel0 = blk * CH_BLOCK;
+	if (rel0 && (rel0 & (WND - 1)) == 0) {
+		/* every 32768 positions retire entries that are out of the window
+		 * so 16-bit positions never alias (cf. slidehash) */
+		const uint32_t stale = (rel0 + 0x8000u) & 0xffffu;
+		for (uint32_t i = lane; i < (1u << HASH_BITS); i += 32) {
+			uint32_t d = (rel0 - S.head[i]) & 0xffffu;
+			if (d >= WND) S.head[i] = (uint16_t) stale;
+		}
+		__syncwarp();
+	}
+	uint32_t hh[4];
+#pragma unroll
+	for (uint32_t j = 0; j < 4; j++) hh[j] = S.hash[blk & 1][32 * j + lane];
+#pragma unroll
+	for (uint32_t j = 0; j < 4; j++) {
+		const uint32_t rel = rel0 + 32 * j + lane;
+		const uint32_t slot = hh[j];
+		/* Two lanes with the same hash in one group of 32 are not rare in text
+		 * (short words, runs).  Fast path: everybody reads the old head, everybody
+		 * stores its own position, and a read-back tells whether any store lost,
+		 * i.e. whether duplicates exist; only then the exact resolution runs. */
+		const uint32_t old = S.head[slot];
+		__syncwarp();
+		S.head[slot] = (uint16_t) rel;
+		__syncwarp();
+		const uint32_t chk = S.head[slot];
+		const bool lost = chk != (rel & 0xffffu);
+		const uint32_t d = (rel - old) & 0xffffu;
+		uint32_t dist = (d < WND && d <= rel) ? d : 0;
+		const unsigned lostmask = __ballot_sync(JDB_FULL_MASK, lost);
+		if (lostmask) {
+			/* lanes involved: the losers and the winners they lost to (the read-back
+			 * names the winner's position).  match_any costs per distinct value, so
+			 * it runs over the involved lanes only. */
+			const unsigned involved = lostmask |
+				__reduce_or_sync(JDB_FULL_MASK, lost ? 1u << ((chk - rel0) & 31u) : 0u);
+			if ((involved >> lane) & 1u) {
+				const unsigned same = __match_any_sync(involved, slot);
+				const unsigned lower = same & ((1u << lane) - 1u);
+				if (lower) dist = lane - (31 - __clz(lower));
+				if ((same >> lane) == 1u) S.head[slot] = (uint16_t) rel;     /* highest lane of its group */
+			}
+			__syncwarp();
+		}
+		if (slot >= CH_DUMMY) dist = 0;
+		S.dist[blk & 1][32 * j + lane] = (uint16_t) dist;
+	}
+}
+
+__global__ void __launch_bounds__(CH_THREADS)
 chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t range,
              uint16_t* __restrict__ prev)
 {
 	JDB_DYN_SMEM(smem_raw);
-	uint16_t* head = (uint16_t*) smem_raw;          /* 2^15 entries */
-	const unsigned lane = threadIdx.x;
+	ChainSmem& S = *(ChainSmem*) smem_raw;
+	const unsigned lane = threadIdx.x & 31u;
+	const bool producer = threadIdx.x < 32;
 
 	const uint64_t r0 = (uint64_t) blockIdx.x * range;
 	if (r0 >= n) return;
@@ -69,88 +183,45 @@ chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, u
 
 	/* positions are handled relative to `start`; an entry holds the low 16
 	 * bits, "empty" is anything that decodes to a distance >= 32768 */
-	for (uint32_t i = lane; i < (1u << HASH_BITS); i += 32) head[i] = 0x8000u;
-	__syncwarp();
+	for (uint32_t i = threadIdx.x; i < (1u << HASH_BITS) + 32; i += CH_THREADS) S.head[i] = 0x8000u;
 
-	/* Input is consumed in blocks of 128 positions: one coalesced 128-byte load
-	 * per block (lane i holds word i), prefetched two blocks ahead so the loop
-	 * never waits for HBM; every lane assembles its 4 bytes with two shuffles. */
 	const uint32_t* words = (const uint32_t*) (in + start);
 	const uint64_t nwords = (n - start + 3) / 4;                 /* words that start before `n` */
 	const uint32_t span = (uint32_t) (r1 - start);
-	const uint32_t nblocks = (span + 127) / 128;
+	const uint32_t nblocks = (span + CH_BLOCK - 1) / CH_BLOCK;
 	const uint32_t hashable = chunk1 - start >= 4 ? (uint32_t) (chunk1 - start - 3) : 0;   /* rel < hashable */
 	const uint32_t emit0 = (uint32_t) (r0 - start);
 
 #define LOADW(blk) ((uint64_t) (blk) * 32 + lane < nwords ? __ldg(words + (uint64_t) (blk) * 32 + lane) : 0u)
-	uint32_t w0 = LOADW(0), w1 = LOADW(1), w2 = LOADW(2);
-	for (uint32_t blk = 0; blk < nblocks; blk++) {
-		const uint32_t w3 = LOADW(blk + 3);
-		const uint32_t rel0 = blk * 128;
-		if (rel0 && (rel0 & (WND - 1)) == 0) {
-			/* every 32768 positions retire entries that are out of the window
-			 * so 16-bit positions never alias (cf. slidehash) */
-			const uint32_t stale = (rel0 + 0x8000u) & 0xffffu;
-			for (uint32_t i = lane; i < (1u << HASH_BITS); i += 32) {
-				uint32_t d = (rel0 - head[i]) & 0xffffu;
-				if (d >= WND) head[i] = (uint16_t) stale;
-			}
-			__syncwarp();
-		}
-		/* hashes of the four groups of 32 first (independent work, off the serial path) */
-		uint32_t hh[4];
-#pragma unroll
-		for (uint32_t j = 0; j < 4; j++) {
-			const uint32_t idx = 8 * j + (lane >> 2);
-			const uint32_t lo = __shfl_sync(JDB_FULL_MASK, w0, idx);
-			uint32_t hi = __shfl_sync(JDB_FULL_MASK, w0, (idx + 1) & 31);
-			if (j == 3) {
-				const uint32_t hn = __shfl_sync(JDB_FULL_MASK, w1, 0);
-				if (idx == 31) hi = hn;
-			}
-			const uint32_t le = __funnelshift_r(lo, hi, (lane & 3u) * 8u);
-			const uint32_t be = __byte_perm(le, 0, 0x0123);
-			hh[j] = (be * HASH_MUL) >> (32 - HASH_BITS);
-		}
-		uint32_t dd[4];
-#pragma unroll
-		for (uint32_t j = 0; j < 4; j++) {
-			const uint32_t rel = rel0 + 32 * j + lane;
-			const bool valid = rel < hashable;
-			/* Two lanes with the same hash in one group of 32 are rare (runs, short
-			 * periods).  Fast path: everybody reads the old head, everybody stores its
-			 * own position, and a read-back tells whether any store lost, i.e. whether
-			 * duplicates exist; only then the exact (slow) match_any resolution runs. */
-			const uint32_t slot = valid ? hh[j] : 0;
-			const uint32_t old = head[slot];
-			__syncwarp();
-			if (valid) head[slot] = (uint16_t) rel;
-			__syncwarp();
-			const bool lost = valid && head[slot] != (uint16_t) rel;
-			uint32_t dist = 0;
-			if (valid) {
-				const uint32_t d = (rel - old) & 0xffffu;
-				if (d < WND && d <= rel) dist = d;
-			}
-			if (__ballot_sync(JDB_FULL_MASK, lost)) {
-				const unsigned same = __match_any_sync(JDB_FULL_MASK, valid ? hh[j] : 0xffffffffu - lane);
-				if (valid) {
-					const unsigned lower = same & ((1u << lane) - 1u);
-					if (lower) dist = lane - (31 - __clz(lower));
-				}
-				__syncwarp();
-				if (valid && (same >> lane) == 1u) head[slot] = (uint16_t) rel;   /* highest lane of its group */
-				__syncwarp();
-			}
-			dd[j] = dist;
-		}
-#pragma unroll
-		for (uint32_t j = 0; j < 4; j++) {
-			const uint32_t rel = rel0 + 32 * j + lane;
-			if (rel >= emit0 && rel < span) prev[start + rel] = (uint16_t) dd[j];
-		}
-		w0 = w1; w1 = w2; w2 = w3;
+	/* four blocks in flight, in four NAMED registers: the round loop is unrolled by
+	 * four so that no register is ever copied while its load is outstanding (a
+	 * rotating w0 = w1 ... would wait for the newest load every round) */
+	uint32_t wa = 0, wb = 0, wc = 0, wd = 0;
+	if (producer) { wa = LOADW(0); wb = LOADW(1); wc = LOADW(2); wd = LOADW(3); }
+	__syncthreads();
+
+#define CH_ROUND(T, WCUR, WNEXT) \
+	do { \
+		const uint32_t t_ = (T); \
+		if (t_ < nblocks + 2) { \
+			if (producer) { \
+				if (t_ < nblocks) chain_hash_block(S, t_, WCUR, WNEXT, hashable, lane); \
+				if (t_ >= 2) chain_emit_block(S, t_ - 2, prev + start, emit0, span, lane); \
+				WCUR = LOADW(t_ + 4); \
+			} else if (t_ >= 1 && t_ <= nblocks) { \
+				chain_link_block(S, t_ - 1, lane); \
+			} \
+		} \
+		__syncthreads(); \
+	} while (0)
+
+	for (uint32_t t = 0; t < nblocks + 2; t += 4) {
+		CH_ROUND(t + 0, wa, wb);
+		CH_ROUND(t + 1, wb, wc);
+		CH_ROUND(t + 2, wc, wd);
+		CH_ROUND(t + 3, wd, wa);
 	}
+#undef CH_ROUND
 #undef LOADW
 }
 
@@ -480,7 +551,7 @@ extern "C" int jdb_lz_chain(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
                             uint16_t* prev, jdb_stream s)
 {
 	if (n == 0) return JDB_OK;
-	const size_t smem = sizeof(uint16_t) << HASH_BITS;
+	const size_t smem = sizeof(ChainSmem);
 #ifndef JDB_SIMT_EMU
 	static int configured[64];
 	int dev = jdb_rt_get_device();
@@ -490,7 +561,7 @@ extern "C" int jdb_lz_chain(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
 	}
 #endif
 	const uint64_t items = (n + range - 1) / range;
-	JDB_LAUNCH(chain_kernel, dim3((unsigned) items), dim3(32), smem, s, in, n, chunk_bytes, range, prev);
+	JDB_LAUNCH(chain_kernel, dim3((unsigned) items), dim3(CH_THREADS), smem, s, in, n, chunk_bytes, range, prev);
 	return jdb_rt_check_launch("chain_kernel");
 }
 
