@@ -36,7 +36,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "-Xptxas", "-v",
-]
+] + os.environ.get("JDB_NVCC_EXTRA", "").split()
 HOST_CFLAGS = ["-std=c99", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wextra",
                "-Wno-unused-parameter", "-D_POSIX_C_SOURCE=200809L"]
 

@@ -233,6 +233,12 @@ chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, u
 #ifndef LZ_WALK_STEPS
 #define LZ_WALK_STEPS 4
 #endif
+#ifndef LZ_TB
+#define LZ_TB 8          /* lanes waiting for COMPARE that trigger the phase */
+#endif
+#ifndef LZ_TC
+#define LZ_TC 8          /* lanes waiting for FETCH that trigger the phase */
+#endif
 #define PER_THREAD   (SEG / LZ_THREADS)            /* 16 */
 #define WALK_BLOCK   256u
 #define WALKERS      (SEG / WALK_BLOCK)            /* 64 */
@@ -371,7 +377,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 			const unsigned bit1 = __ballot_sync(JDB_FULL_MASK, mode & 2u);
 			const unsigned walkers = bit0 & ~bit1, comparers = bit1 & ~bit0, fetchers = ~(bit0 | bit1);
 			if ((bit0 & bit1) == JDB_FULL_MASK) break;
-			if (comparers && (walkers == 0 || __popc(comparers) >= 8)) {
+			if (comparers && (walkers == 0 || __popc(comparers) >= LZ_TB)) {
 				if (mode == M_COMPARE) {
 					uint32_t len = clen;
 					bool done = false;
@@ -401,7 +407,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 					}
 				}
 			}
-			if (fetchers && (walkers == 0 || __popc(fetchers) >= 8)) {
+			if (fetchers && (walkers == 0 || __popc(fetchers) >= LZ_TC)) {
 				uint32_t base = 0;
 				const uint32_t leader = (uint32_t) __ffs((int) fetchers) - 1;
 				if (lane == leader) base = atomicAdd(&S.next_pos, (uint32_t) __popc(fetchers));

@@ -1,5 +1,5 @@
 """Quick GPU check of the deflate pipeline through the C ABI (device-resident buffers)."""
-import sys, pathlib, time, zlib, ctypes as C
+import sys, pathlib, time, zlib, os, ctypes as C
 R = pathlib.Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(R)); sys.path.insert(0, str(R / "tests"))
 import numpy as np, torch
@@ -9,7 +9,7 @@ from jdeflate_b200 import api
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 levels = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [6]
 kinds = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 2, 3, 5]
-jd = api.load(); c = Corpus(); o = Oracle()
+jd = api.load(os.environ.get('JDB200_LIB')); c = Corpus(); o = Oracle()
 n = mib << 20
 for kind in kinds:
     host = np.empty(n, np.uint8)
