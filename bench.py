@@ -268,14 +268,16 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    # clocks are sampled from before the warm-up steps (same load) to the end of the timed region:
+    # nvidia-smi needs ~1 s to deliver its first sample, longer than a short timed region
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
 
     # ---- timed region: device-resident ----------------------------------------------------------
-    sampler = ClockSampler(local)
     jd.profile(True)
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):

@@ -65,6 +65,7 @@ int   jdb_event_create(jdb_event* e);
 void  jdb_event_destroy(jdb_event e);
 int   jdb_event_record(jdb_event e, jdb_stream s);
 int   jdb_stream_wait_event(jdb_stream s, jdb_event e);
+int   jdb_event_sync(jdb_event e);              /* host waits for the event */
 
 /* ---- checksums (checksum.cu) ------------------------------------------ */
 /*

@@ -177,6 +177,11 @@ extern "C" int jdb_event_record(jdb_event e, jdb_stream s)
 	return check(cudaEventRecord((cudaEvent_t) e, (cudaStream_t) s), "cudaEventRecord");
 }
 
+extern "C" int jdb_event_sync(jdb_event e)
+{
+	return check(cudaEventSynchronize((cudaEvent_t) e), "cudaEventSynchronize");
+}
+
 extern "C" int jdb_stream_wait_event(jdb_stream s, jdb_event e)
 {
 	return check(cudaStreamWaitEvent((cudaStream_t) s, (cudaEvent_t) e, 0), "cudaStreamWaitEvent");

@@ -44,32 +44,49 @@ struct TDEFLTPblc {
 	uint8* tend;
 };
 
+/* one batch in flight: FREE -> (filled) -> RUNNING -> DRAINING -> FREE */
+enum { SLOT_FREE = 0, SLOT_RUNNING = 1, SLOT_DRAINING = 2 };
+
+struct jdb_slot {
+	jdb_dbuf stage;         /* gathered input (host sources)                     */
+	size_t   stagelen;
+	jdb_dbuf work;          /* pipeline workspace, holds the compressed bytes    */
+	const uint8* out;       /* compressed bytes of the batch (device)            */
+	uint64_t* htotal;       /* pinned: compressed size, valid after `done`       */
+	jdb_event done;
+	size_t   outlen;
+	size_t   outpos;
+	int      state;
+	int      closes;        /* carries the flush / end marker of the request     */
+	int      inplace;       /* reads the caller's device memory                  */
+};
+
 struct TDEFLTPrvt {
 	struct TDEFLTPblc public;
 
 	const TAllocator* allctr;
 	int32  level;
 	uint32 used;
-	uint32 closed;          /* the final marker has been produced */
+	uint32 closed;          /* the marker of the current request has been written */
+	uint32 closing;         /* ... has been launched                               */
 
 	jdb_deflate_cfg cfg;
 	size_t batchcap;
 
+	/* two batches overlap: while one runs on `stream`, the other one's input is
+	 * gathered (H2D) and the previous one's output is drained (D2H) on `cstream` */
 	jdb_stream stream;
-	jdb_dbuf   stage;       /* gathered input */
-	size_t     stagelen;
-	jdb_dbuf   work;
-
-	const uint8* outptr;    /* compressed bytes of the last batch (device) */
-	size_t  outlen;
-	size_t  outpos;
-
-	uint64_t* htotal;       /* pinned */
+	jdb_stream cstream;
+	struct jdb_slot slot[2];
+	int fil;                /* slot receiving input                              */
+	int fifo[2];            /* launch order of the RUNNING slots                 */
+	int nfifo;
+	int drn;                /* slot being drained, -1 none                       */
 
 	/* checksums of the uncompressed bytes for zstrm */
 	int       checks;       /* JDB_CK_* mask */
 	uint32_t* dchecks;      /* device: [0] crc register, [1] adler */
-	uint32_t* hchecks;      /* pinned mirror */
+	uint32_t* hchecks;      /* pinned mirror              */
 	jdb_dbuf  ckwork;
 };
 
@@ -139,13 +156,21 @@ deflator_create(uintxx flags, intxx level, const TAllocator* allctr)
 	PRVT->batchcap = env_size("JDB200_BATCH_MIB", DEFAULT_BATCH >> 20) << 20;
 	PRVT->batchcap = (PRVT->batchcap + chunk - 1) / chunk * chunk;
 
-	if (jdb_stream_create(&PRVT->stream) != JDB_OK) {
+	if (jdb_stream_create(&PRVT->stream) != JDB_OK || jdb_stream_create(&PRVT->cstream) != JDB_OK) {
 		goto L_FAIL;
 	}
-	PRVT->htotal = jdb_pinned_alloc(64);
+	{
+		int i;
+		for (i = 0; i < 2; i++) {
+			PRVT->slot[i].htotal = jdb_pinned_alloc(64);
+			if (PRVT->slot[i].htotal == NULL || jdb_event_create(&PRVT->slot[i].done) != JDB_OK) {
+				goto L_FAIL;
+			}
+		}
+	}
 	PRVT->hchecks = jdb_pinned_alloc(64);
 	PRVT->dchecks = jdb_dev_alloc(64);
-	if (PRVT->htotal == NULL || PRVT->hchecks == NULL || PRVT->dchecks == NULL) {
+	if (PRVT->hchecks == NULL || PRVT->dchecks == NULL) {
 		goto L_FAIL;
 	}
 	deflator_reset(state);
@@ -171,10 +196,24 @@ deflator_reset(TDeflator* state)
 
 	PRVT->used = 0;
 	PRVT->closed = 0;
-	PRVT->stagelen = 0;
-	PRVT->outptr = NULL;
-	PRVT->outlen = 0;
-	PRVT->outpos = 0;
+	PRVT->closing = 0;
+	if (PRVT->stream) {
+		/* nothing of an abandoned request may still be running */
+		jdb_stream_sync(PRVT->stream);
+		jdb_stream_sync(PRVT->cstream);
+	}
+	{
+		int i;
+		for (i = 0; i < 2; i++) {
+			PRVT->slot[i].stagelen = 0;
+			PRVT->slot[i].outlen = PRVT->slot[i].outpos = 0;
+			PRVT->slot[i].state = SLOT_FREE;
+			PRVT->slot[i].closes = PRVT->slot[i].inplace = 0;
+		}
+	}
+	PRVT->fil = 0;
+	PRVT->nfifo = 0;
+	PRVT->drn = -1;
 	if (PRVT->hchecks) {
 		PRVT->hchecks[0] = 0xffffffffu;
 		PRVT->hchecks[1] = 1u;
@@ -194,13 +233,23 @@ deflator_destroy(TDeflator* state)
 	if (PRVT->stream) {
 		jdb_stream_sync(PRVT->stream);
 	}
-	jdb_dbuf_release(&PRVT->stage);
-	jdb_dbuf_release(&PRVT->work);
+	if (PRVT->cstream) {
+		jdb_stream_sync(PRVT->cstream);
+	}
+	{
+		int i;
+		for (i = 0; i < 2; i++) {
+			jdb_dbuf_release(&PRVT->slot[i].stage);
+			jdb_dbuf_release(&PRVT->slot[i].work);
+			jdb_pinned_free(PRVT->slot[i].htotal);
+			jdb_event_destroy(PRVT->slot[i].done);
+		}
+	}
 	jdb_dbuf_release(&PRVT->ckwork);
-	jdb_pinned_free(PRVT->htotal);
 	jdb_pinned_free(PRVT->hchecks);
 	jdb_dev_free(PRVT->dchecks);
 	jdb_stream_destroy(PRVT->stream);
+	jdb_stream_destroy(PRVT->cstream);
 	a = PRVT->allctr;
 	a->dispose(state, sizeof(struct TDEFLTPrvt), a->user);
 }
@@ -263,17 +312,18 @@ validate(struct TDEFLTPrvt* state)
 	return 1;
 }
 
-/* one pipeline launch over in[0..n) (device memory); blocks until the size is known */
+/* queue one pipeline launch over in[0..n) (device memory) on the compute stream */
 static int
-compress_batch(struct TDEFLTPrvt* state, const uint8* in, size_t n, int final)
+launch_batch(struct TDEFLTPrvt* state, int k, const uint8* in, size_t n, int closes, int inplace)
 {
+	struct jdb_slot* sl = &PRVT->slot[k];
 	size_t need;
 	uint8_t* out;
 	uint64_t* dtotal;
 
-	PRVT->cfg.final = (uint32_t) final;
+	PRVT->cfg.final = (uint32_t) (closes && PBLC->flush == DEFLT_END);
 	need = jdb_deflate_workspace_bytes(n, &PRVT->cfg);
-	if (need == 0 || jdb_dbuf_reserve(&PRVT->work, need) != 0) {
+	if (need == 0 || jdb_dbuf_reserve(&sl->work, need) != 0) {
 		return -1;
 	}
 	if (PRVT->checks && n) {
@@ -285,16 +335,94 @@ compress_batch(struct TDEFLTPrvt* state, const uint8* in, size_t n, int final)
 			return -1;
 		}
 	}
-	if (jdb_deflate_run(in, n, &PRVT->cfg, PRVT->work.ptr, &out, &dtotal, PRVT->stream) != JDB_OK) {
+	if (jdb_deflate_run(in, n, &PRVT->cfg, sl->work.ptr, &out, &dtotal, PRVT->stream) != JDB_OK) {
 		return -1;
 	}
-	if (jdb_copy_async(PRVT->htotal, dtotal, 8, PRVT->stream) != JDB_OK ||
-	    jdb_stream_sync(PRVT->stream) != JDB_OK) {
+	if (jdb_copy_async(sl->htotal, dtotal, 8, PRVT->stream) != JDB_OK ||
+	    jdb_event_record(sl->done, PRVT->stream) != JDB_OK) {
 		return -1;
 	}
-	PRVT->outptr = out;
-	PRVT->outlen = (size_t) PRVT->htotal[0];
-	PRVT->outpos = 0;
+	sl->out = out;
+	sl->outlen = 0;
+	sl->outpos = 0;
+	sl->state = SLOT_RUNNING;
+	sl->closes = closes;
+	sl->inplace = inplace;
+	sl->stagelen = 0;           /* the stage buffer itself is read by the kernels until `done` */
+	PRVT->fifo[PRVT->nfifo++] = k;
+	return 0;
+}
+
+/* wait for the oldest running batch; it becomes the one being drained */
+static int
+retire_oldest(struct TDEFLTPrvt* state)
+{
+	int k = PRVT->fifo[0];
+	struct jdb_slot* sl = &PRVT->slot[k];
+
+	if (jdb_event_sync(sl->done) != JDB_OK) {
+		return -1;
+	}
+	PRVT->fifo[0] = PRVT->fifo[1];
+	PRVT->nfifo--;
+	sl->outlen = (size_t) sl->htotal[0];
+	sl->outpos = 0;
+	sl->state = SLOT_DRAINING;
+	PRVT->drn = k;
+	return 0;
+}
+
+/* batches that read the caller's device memory must be done before we return */
+static int
+settle_inplace(struct TDEFLTPrvt* state)
+{
+	int i;
+
+	for (i = 0; i < PRVT->nfifo; i++) {
+		struct jdb_slot* sl = &PRVT->slot[PRVT->fifo[i]];
+		if (sl->inplace && jdb_event_sync(sl->done) != JDB_OK) {
+			return -1;
+		}
+	}
+	return 0;
+}
+
+/* grow the stage buffer of a slot (contents preserved) */
+static int
+stage_reserve(struct TDEFLTPrvt* state, struct jdb_slot* sl, size_t want)
+{
+	jdb_dbuf bigger;
+	size_t cap;
+
+	if (sl->stage.ptr != NULL && sl->stage.cap >= want) {
+		return 0;
+	}
+	cap = sl->stage.cap ? sl->stage.cap * 2 : ((size_t) 1 << 20);
+	while (cap < want) {
+		cap *= 2;
+	}
+	if (cap > PRVT->batchcap) {
+		cap = PRVT->batchcap;
+	}
+	bigger.ptr = NULL;
+	bigger.cap = 0;
+	if (jdb_dbuf_reserve(&bigger, cap) != 0) {
+		return -1;
+	}
+	if (sl->stagelen) {
+		if (jdb_copy_async(bigger.ptr, sl->stage.ptr, sl->stagelen, PRVT->cstream) != JDB_OK ||
+		    jdb_stream_sync(PRVT->cstream) != JDB_OK) {
+			jdb_dbuf_release(&bigger);
+			return -1;
+		}
+	}
+	/* the old buffer may still be read by a batch launched from it */
+	if (PRVT->nfifo && jdb_stream_sync(PRVT->stream) != JDB_OK) {
+		jdb_dbuf_release(&bigger);
+		return -1;
+	}
+	jdb_dbuf_release(&sl->stage);
+	sl->stage = bigger;
 	return 0;
 }
 
@@ -323,30 +451,42 @@ deflator_deflate(TDeflator* state, eDEFLTFlush flush)
 	PRVT->used = 1;
 
 	for (;;) {
+		struct jdb_slot* fs;
 		size_t srcleft;
+		int all_in;
 
-		/* 1. drain what the last batch produced */
-		if (PRVT->outpos < PRVT->outlen) {
+		/* 1. drain the compressed bytes of the oldest finished batch */
+		if (PRVT->drn >= 0) {
+			struct jdb_slot* sl = &PRVT->slot[PRVT->drn];
 			size_t room = (size_t) (PBLC->tend - PBLC->target);
-			size_t n = PRVT->outlen - PRVT->outpos;
+			size_t n = sl->outlen - sl->outpos;
 			if (n > room) {
 				n = room;
 			}
 			if (n) {
-				if (jdb_copy_async(PBLC->target, PRVT->outptr + PRVT->outpos, n, PRVT->stream) != JDB_OK ||
-				    jdb_stream_sync(PRVT->stream) != JDB_OK) {
+				if (jdb_copy_async(PBLC->target, sl->out + sl->outpos, n, PRVT->cstream) != JDB_OK ||
+				    jdb_stream_sync(PRVT->cstream) != JDB_OK) {
 					goto L_FAIL;
 				}
 				PBLC->target += n;
-				PRVT->outpos += n;
+				sl->outpos += n;
 			}
-			if (PRVT->outpos < PRVT->outlen) {
+			if (sl->outpos < sl->outlen) {
+				if (settle_inplace(PRVT) != 0) {
+					goto L_FAIL;
+				}
 				return (eDEFLTResult) (PBLC->status = DEFLT_TGTEXHSTD);
 			}
+			if (sl->closes) {
+				PRVT->closed = 1;
+			}
+			sl->state = SLOT_FREE;
+			PRVT->drn = -1;
 		}
 
 		/* 2. everything requested has been written */
 		if (PRVT->closed) {
+			PRVT->closing = 0;
 			if (PBLC->flush == DEFLT_FLUSH) {
 				/* keep going on the same instance (src/deflator.c:763-768) */
 				PBLC->flush = 0;
@@ -358,73 +498,86 @@ deflator_deflate(TDeflator* state, eDEFLTFlush flush)
 			return (eDEFLTResult) (PBLC->status = DEFLT_OK);
 		}
 
+		fs = &PRVT->slot[PRVT->fil];
 		srcleft = (size_t) (PBLC->send - PBLC->source);
 
-		/* 3. large device-resident input is compressed in place */
-		if (PRVT->stagelen == 0 && srcleft &&
-		    (PBLC->flush || srcleft >= PRVT->batchcap) &&
-		    ((uintptr_t) PBLC->source & 15) == 0 && jdb_ptr_is_device(PBLC->source)) {
-			size_t n = srcleft;
-			int last;
-			if (n > PRVT->batchcap) {
-				n = PRVT->batchcap;
+		if (fs->state == SLOT_FREE && !PRVT->closing) {
+			/* 3. large device-resident input is compressed in place */
+			if (fs->stagelen == 0 && srcleft &&
+			    (PBLC->flush || srcleft >= PRVT->batchcap) &&
+			    ((uintptr_t) PBLC->source & 15) == 0 && jdb_ptr_is_device(PBLC->source)) {
+				size_t n = srcleft;
+				int last;
+				if (n > PRVT->batchcap) {
+					n = PRVT->batchcap;
+				}
+				last = PBLC->flush && n == srcleft;
+				if (launch_batch(PRVT, PRVT->fil, PBLC->source, n, last, 1) != 0) {
+					goto L_FAIL;
+				}
+				PBLC->source += n;
+				if (last) {
+					PRVT->closing = 1;
+				}
+				PRVT->fil ^= 1;
+				continue;
 			}
-			last = PBLC->flush && n == srcleft;
-			if (compress_batch(PRVT, PBLC->source, n, last && PBLC->flush == DEFLT_END) != 0) {
-				goto L_FAIL;
+
+			/* 4. gather into the staging batch */
+			if (srcleft) {
+				size_t room = PRVT->batchcap - fs->stagelen;
+				if (srcleft > room) {
+					srcleft = room;
+				}
+				if (srcleft) {
+					if (stage_reserve(PRVT, fs, fs->stagelen + srcleft) != 0) {
+						goto L_FAIL;
+					}
+					/* the caller may reuse its buffer as soon as we return: wait for
+					 * the copy (only the copy -- a running batch keeps running) */
+					if (jdb_copy_async(fs->stage.ptr + fs->stagelen, PBLC->source, srcleft, PRVT->cstream) != JDB_OK ||
+					    jdb_stream_sync(PRVT->cstream) != JDB_OK) {
+						goto L_FAIL;
+					}
+					PBLC->source += srcleft;
+					fs->stagelen += srcleft;
+				}
 			}
-			PBLC->source += n;
-			if (last) {
-				PRVT->closed = 1;
+
+			/* 5. queue the pipeline when the batch is full or a flush is due */
+			all_in = PBLC->source == PBLC->send;
+			if (fs->stagelen == PRVT->batchcap || (PBLC->flush && all_in)) {
+				int last = PBLC->flush && all_in;
+				if (fs->stage.ptr == NULL && stage_reserve(PRVT, fs, 4096) != 0) {
+					goto L_FAIL;
+				}
+				if (launch_batch(PRVT, PRVT->fil, fs->stage.ptr, fs->stagelen, last, 0) != 0) {
+					goto L_FAIL;
+				}
+				if (last) {
+					PRVT->closing = 1;
+				}
+				PRVT->fil ^= 1;
+				continue;
+			}
+			if (all_in) {
+				if (settle_inplace(PRVT) != 0) {
+					goto L_FAIL;
+				}
+				return (eDEFLTResult) (PBLC->status = DEFLT_SRCEXHSTD);
 			}
 			continue;
 		}
 
-		/* 4. gather into the staging batch */
-		if (srcleft) {
-			size_t room;
-			if (jdb_dbuf_reserve(&PRVT->stage, PRVT->batchcap) != 0 && PRVT->stagelen == 0) {
-				goto L_FAIL;
-			}
-			if (PRVT->stage.ptr == NULL) {
-				goto L_FAIL;
-			}
-			room = PRVT->batchcap - PRVT->stagelen;
-			if (srcleft > room) {
-				srcleft = room;
-			}
-			if (jdb_copy_async(PRVT->stage.ptr + PRVT->stagelen, PBLC->source, srcleft, PRVT->stream) != JDB_OK) {
-				goto L_FAIL;
-			}
-			/* the caller may reuse its buffer as soon as we return */
-			if (jdb_stream_sync(PRVT->stream) != JDB_OK) {
-				goto L_FAIL;
-			}
-			PBLC->source += srcleft;
-			PRVT->stagelen += srcleft;
+		/* 6. no slot to fill (or the request is already closing): wait for the
+		 * oldest batch in flight; its output is drained next */
+		if (PRVT->nfifo == 0) {
+			PBLC->error = DEFLT_EBADSTATE;
+			PBLC->state = POISON;
+			return DEFLT_ERROR;
 		}
-
-		/* 5. run the pipeline when the batch is full or a flush is due */
-		{
-			int all_in = PBLC->source == PBLC->send;
-			int full = PRVT->stagelen == PRVT->batchcap;
-			if (full || (PBLC->flush && all_in)) {
-				int last = PBLC->flush && all_in;
-				if (PRVT->stage.ptr == NULL && jdb_dbuf_reserve(&PRVT->stage, 4096) != 0) {
-					goto L_FAIL;
-				}
-				if (compress_batch(PRVT, PRVT->stage.ptr, PRVT->stagelen, last && PBLC->flush == DEFLT_END) != 0) {
-					goto L_FAIL;
-				}
-				PRVT->stagelen = 0;
-				if (last) {
-					PRVT->closed = 1;
-				}
-				continue;
-			}
-			if (all_in) {
-				return (eDEFLTResult) (PBLC->status = DEFLT_SRCEXHSTD);
-			}
+		if (retire_oldest(PRVT) != 0) {
+			goto L_FAIL;
 		}
 	}
 

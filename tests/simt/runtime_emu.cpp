@@ -48,6 +48,7 @@ extern "C" int jdb_event_create(jdb_event* e) { *e = (jdb_event) 1; return JDB_O
 extern "C" void jdb_event_destroy(jdb_event) {}
 extern "C" int jdb_event_record(jdb_event, jdb_stream) { return JDB_OK; }
 extern "C" int jdb_stream_wait_event(jdb_stream, jdb_event) { return JDB_OK; }
+extern "C" int jdb_event_sync(jdb_event) { return JDB_OK; }
 
 extern "C" int  jdb_prof_begin(const char*, jdb_stream) { return -1; }
 extern "C" void jdb_prof_end(int, jdb_stream) {}

@@ -143,3 +143,22 @@ def test_reset_reuses_instance(lib, oracle, corpus):
             de.reset()
     finally:
         de.close()
+
+
+def test_multi_batch_pipeline(lib, oracle, corpus, monkeypatch):
+    """Several internal batches (two in flight, output drained in order) with small source pieces
+    and target windows: the stream must be the same as with one big window."""
+    monkeypatch.setenv("JDB200_BATCH_MIB", "1")
+    d = corpus.fill(5, (2 << 20) + 12345, offset=(4 << 20) - (1 << 20))
+    whole = lib.deflate_bytes(d, 6)
+    check_stream(oracle, whole, d)
+    z = lib.deflate_bytes(d, 6, feed=300000, window=77777)
+    assert z == whole
+    # a sync flush in the middle of a batch, then more input
+    de = lib.deflator(6)
+    try:
+        za = de.run(d[:1500000], flush=api.DEFLT_FLUSH, window=500000)
+        zb = de.run(d[1500000:], flush=api.DEFLT_END, window=500000)
+    finally:
+        de.close()
+    check_stream(oracle, za + zb, d)
