@@ -156,7 +156,7 @@ def cpu_sample_size(cores, total):
     return n - n % (12 * MIB) if n >= 12 * MIB else n
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, real_stdout=sys.stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -184,7 +184,7 @@ def run_reference_arm(args):
         "inflate": {"value": round(inf_gbs, 4), "unit": "GB/s", "note": "reference TInflator per core on its own L%d slices" % args.level},
         "ratio": round(sample / comp, 4), "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=real_stdout, flush=True)
     return 0
 
 
@@ -202,7 +202,24 @@ def workload_config(args, extra=None):
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 
+def _claim_stdout():
+    """Everything any library prints to fd 1 during the run (NCCL's version banner, for one) goes
+    to stderr; the returned file object is the real stdout, used once for the JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    real_stdout = _claim_stdout()
+    try:
+        return _main(real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(real_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -219,7 +236,7 @@ def main():
         log("note: the timing rules ask for >= 3 warm-up steps")
 
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, real_stdout)
 
     import numpy as np
     import torch
@@ -433,7 +450,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "inflate": inflate,
             "gpu_launches": launches, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     d.close()
     if dist is not None:
         dist.destroy_process_group()
