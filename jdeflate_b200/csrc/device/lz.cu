@@ -233,11 +233,11 @@ chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, u
 #ifndef LZ_WALK_STEPS
 #define LZ_WALK_STEPS 4
 #endif
-#ifndef LZ_TB
-#define LZ_TB 8          /* lanes waiting for COMPARE that trigger the phase */
+#ifndef LZ_GRAB
+#define LZ_GRAB 128u        /* positions a warp takes from the segment at a time */
 #endif
-#ifndef LZ_TC
-#define LZ_TC 8          /* lanes waiting for FETCH that trigger the phase */
+#ifndef LZ_CMP_WORDS
+#define LZ_CMP_WORDS 2   /* 32-bit words compared per COMPARE phase */
 #endif
 #define PER_THREAD   (SEG / LZ_THREADS)            /* 16 */
 #define WALK_BLOCK   256u
@@ -356,6 +356,8 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 		uint32_t mode = M_FETCH;
 		uint32_t p = 0xffffffffu, j = 0, jmin = 0, maxlen = 0, best = 0, bestd = 0, cur = 0, steps = 0, cb = 0;
 		uint32_t cq = 0, clen = 0, dmax = 0;
+		/* positions are handed out in blocks of LZ_GRAB per warp */
+		uint32_t wnext = 0, wend = 0;
 		for (;;) {
 			/* a few chain steps per round amortise the phase bookkeeping below; a lane
 			 * that leaves WALK mode sits out the remaining steps */
@@ -375,14 +377,14 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 			/* mode bits: FETCH 00, WALK 01, COMPARE 10, DONE 11 */
 			const unsigned bit0 = __ballot_sync(JDB_FULL_MASK, mode & 1u);
 			const unsigned bit1 = __ballot_sync(JDB_FULL_MASK, mode & 2u);
-			const unsigned walkers = bit0 & ~bit1, comparers = bit1 & ~bit0, fetchers = ~(bit0 | bit1);
 			if ((bit0 & bit1) == JDB_FULL_MASK) break;
-			if (comparers && (walkers == 0 || __popc(comparers) >= LZ_TB)) {
+			if (bit1 & ~bit0) {
+				/* COMPARE: 8 more bytes of the candidate (most comparisons end here) */
 				if (mode == M_COMPARE) {
 					uint32_t len = clen;
 					bool done = false;
 #pragma unroll
-					for (int u = 0; u < 4; u++) {
+					for (int u = 0; u < LZ_CMP_WORDS; u++) {
 						if (!done) {
 							if (len >= maxlen) done = true;
 							else {
@@ -407,15 +409,32 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 					}
 				}
 			}
-			if (fetchers && (walkers == 0 || __popc(fetchers) >= LZ_TC)) {
-				uint32_t base = 0;
-				const uint32_t leader = (uint32_t) __ffs((int) fetchers) - 1;
-				if (lane == leader) base = atomicAdd(&S.next_pos, (uint32_t) __popc(fetchers));
-				base = __shfl_sync(JDB_FULL_MASK, base, leader);
-				if (fetchers & (1u << lane)) {
+			const unsigned fetchers = ~(bit0 | bit1) | __ballot_sync(JDB_FULL_MASK, mode == M_FETCH);
+			if (fetchers) {
+				/* FETCH: positions come from the warp's own range; the counter lives in a
+				 * register (the phase is warp-synchronous), ranks from the ballot */
+				if (wnext == wend && wend < SEG) {
+					/* the warp's block is used up: take the next LZ_GRAB positions of the
+					 * segment (one shared-memory atomic per block keeps the warps level) */
+					uint32_t g = 0;
+					if (lane == 0) g = atomicAdd(&S.next_pos, LZ_GRAB);
+					g = __shfl_sync(JDB_FULL_MASK, g, 0);
+					wnext = g < SEG ? g : SEG;
+					wend = g < SEG ? g + LZ_GRAB : SEG;
+				}
+				const uint32_t base = wnext;
+				const uint32_t rank = (uint32_t) __popc(fetchers & ((1u << lane) - 1u));
+				const uint32_t have = wend - wnext;
+				const uint32_t want = (uint32_t) __popc(fetchers);
+				wnext += want < have ? want : have;
+				if ((fetchers >> lane) & 1u) {
 					if (p != 0xffffffffu) S.m[p] = best >= MINLEN ? (best << 16) | bestd : 0;
-					p = base + (uint32_t) __popc(fetchers & ((1u << lane) - 1u));
-					if (p >= SEG) { mode = M_DONE; p = 0xffffffffu; }
+					p = base + rank;
+					if (rank >= have) {
+						/* block exhausted: next round (or done when the segment is) */
+						if (wend >= SEG) mode = M_DONE;
+						p = 0xffffffffu;
+					}
 					else if (p >= seg_len || seg_len - p < MINLEN) {
 						/* nothing to find here; stay in FETCH */
 						S.m[p] = 0;
