@@ -44,6 +44,7 @@
  * + <= 4 B tokens written.
  */
 #include "deflate.cuh"
+#include <stdlib.h>
 
 #define HASH_BITS      14
 #define HASH_MUL       0x1e35a7bdu
@@ -255,6 +256,7 @@ extern "C" { uint32_t* jdb_emu_lz_iters = 0; uint8_t* jdb_emu_lz_steps = 0; uint
 
 struct LzParams {
 	uint32_t good, nice, chain, lazy;
+	uint32_t short3;                 /* probe short distances for 3-byte matches */
 };
 
 struct LzSmem {
@@ -268,7 +270,10 @@ struct LzSmem {
 	uint32_t merge[WALKERS];
 	uint32_t warp_sum[LZ_THREADS / 32];
 	uint32_t next_pos;               /* work distribution of the match search */
+	uint32_t nomatch;                /* positions without a match (3-byte probe switch) */
 };
+
+__constant__ uint8_t c_short_dist[12] = { 1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64 };
 
 static __device__ __forceinline__ uint32_t ilog2_u32(uint32_t v) { return 31 - __clz(v); }
 
@@ -333,7 +338,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 			const uint32_t d = prev[hist0 + i];
 			S.prev[i] = (uint16_t) ((d && d <= i) ? i - d : 0xffffu);
 		}
-		if (tid == 0) S.next_pos = 0;
+		if (tid == 0) { S.next_pos = 0; S.nomatch = 0; }
 		for (uint32_t i = tid; i < SEG / 32; i += LZ_THREADS) { S.spec[i] = 0; S.fix[i] = 0; }
 		for (uint32_t i = tid; i < NSYM; i += LZ_THREADS) S.hist[i] = 0;
 	}
@@ -454,6 +459,41 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 		}
 	}
 	__syncthreads();
+
+	/* ---- 3-byte matches ------------------------------------------------------
+	 * The hash-4 chains cannot see them.  The reference finds them with a second,
+	 * 3-byte hash table when literals dominate (getmatch2, src/deflator.c:2676-2711:
+	 * at most two probes, only offsets <= 8192).  Here positions that found
+	 * nothing probe a fixed set of short distances instead -- the strides of
+	 * record-structured binary data, which is where such matches occur. */
+	if (prm.short3) {
+		/* only where literals dominate (the reference's doshortmatches switch,
+		 * src/deflator.c:2928-2933): more than 40 % of the positions found nothing */
+		uint32_t nomatch = 0;
+		for (uint32_t k = 0; k < PER_THREAD; k++) {
+			const uint32_t p = tid + k * LZ_THREADS;
+			nomatch += (p < seg_len && S.m[p] == 0) ? 1u : 0u;
+		}
+		for (int o = 16; o; o >>= 1) nomatch += __shfl_xor_sync(JDB_FULL_MASK, nomatch, o);
+		if ((tid & 31u) == 0) atomicAdd(&S.nomatch, nomatch);
+		__syncthreads();
+	}
+	if (prm.short3 && (prm.short3 > 1 || S.nomatch * 5u > seg_len * 2u)) {
+		for (uint32_t k = 0; k < PER_THREAD; k++) {
+			const uint32_t p = tid + k * LZ_THREADS;
+			if (p + 3 > seg_len || S.m[p] != 0) continue;
+			const uint32_t j = hoff + p;
+			const uint32_t w = jdb_ld32u(S.data, j) & 0xffffffu;
+			uint32_t found = 0;
+#pragma unroll
+			for (int u = 0; u < 12; u++) {
+				const uint32_t d = c_short_dist[u];
+				if (!found && d <= j && (jdb_ld32u(S.data, j - d) & 0xffffffu) == w) found = d;
+			}
+			if (found) S.m[p] = (3u << 16) | found;
+		}
+		__syncthreads();
+	}
 
 	/* ---- per position: would a parser arriving here take the match? ---- */
 	for (uint32_t k = 0; k < PER_THREAD; k++) {
@@ -606,6 +646,7 @@ extern "C" int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
 #endif
 	LzParams prm;
 	prm.good = good; prm.nice = nice; prm.chain = chain; prm.lazy = lazy;
+	prm.short3 = getenv("JDB_LZ_SHORT3") ? (uint32_t) atoi(getenv("JDB_LZ_SHORT3")) : 1u;
 	const uint64_t nseg = (n + SEG - 1) / SEG;
 	JDB_LAUNCH(lz_kernel, dim3((unsigned) nseg), dim3(LZ_THREADS), smem, s,
 	           in, n, chunk_bytes, prev, prm, tok, seg_ntok, seg_hist);
