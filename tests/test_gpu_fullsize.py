@@ -94,3 +94,73 @@ def test_batched_inflate_quarter_million_records(jd, corpus):
     for k in range(0, count, 4099):
         o, ln = int(items[k, 1]), int(items[k, 3])
         assert host[o:o + ln].tobytes() == recs[perm[k]]
+
+
+@pytest.mark.parametrize("level", [1, 6])
+def test_zstrm_gzip_streaming_8mib_callbacks(jd, corpus, level):
+    """BASELINE config 5: gzip through zstrm_deflate in 8 MiB calls, back through zstrm_inflate with
+    a source callback and 8 MiB reads; third-party check with Python's zlib."""
+    n = 96 * MIB
+    data = corpus.fill(5, n, offset=(4 << 20) - 12345)
+    out = bytearray()
+    z = jd.zstrm(api.ZSTRM_DEFLATE | api.ZSTRM_GZIP, level)
+    try:
+        z.settargetfn(lambda b: (out.extend(b), len(b))[1])
+        view = memoryview(data)
+        for off in range(0, n, 8 * MIB):
+            piece = bytes(view[off:off + 8 * MIB])
+            assert z.deflate(piece) == len(piece)
+        z.flush(1)
+        assert (z.error, z.state) == (0, 4) and z.s.total == n and z.s.crc == zlib.crc32(data)
+    finally:
+        z.close()
+    comp = bytes(out)
+    assert zlib.decompress(comp, 31) == data
+    pos = {"p": 0}
+
+    def rd(size):
+        k = min(size, 8 * MIB, len(comp) - pos["p"])
+        b = comp[pos["p"]: pos["p"] + k]
+        pos["p"] += k
+        return b
+    zi = jd.zstrm(api.ZSTRM_INFLATE)
+    try:
+        zi.setsourcefn(rd)
+        crc, total = 0, 0
+        while zi.state != 4:
+            b = zi.inflate(8 * MIB)
+            if not b:
+                break
+            crc = zlib.crc32(b, crc)
+            total += len(b)
+        assert (zi.error, total, crc) == (0, n, zlib.crc32(data)) and zi.s.usedinput == len(comp)
+    finally:
+        zi.close()
+
+
+def test_zlib_level9_logs_sharded_two_ranks(jd, oracle, corpus):
+    """BASELINE config 4 shape: zlib level 9 of LOGS, contiguous chunk-aligned slices per rank
+    (two ranks emulated one after the other on this GPU), the 24-byte exchange replaced by
+    shard.combine(); the concatenation is one zlib stream with the right Adler-32, and its size is
+    within 3 % of the reference encoder at level 9 on the same bytes."""
+    from jdeflate_b200 import shard
+    n = 24 * MIB
+    data = corpus.fill(1, n, offset=777)
+    rows, parts = [], []
+    for rank in range(2):
+        pl = shard.plan(n, 2, rank)
+        piece = data[pl.begin:pl.end]
+        d = jd.deflator(9)
+        try:
+            parts.append(d.run(piece, flush=api.DEFLT_END if pl.last else api.DEFLT_FLUSH))
+        finally:
+            d.close()
+        rows.append((len(parts[-1]), jd.adler32(piece), len(piece), "adler32"))
+    offsets, total, adler, raw = shard.combine(rows)
+    assert offsets == [0, len(parts[0])] and raw == n and adler == zlib.adler32(data)
+    stream = bytes([0x78, 0xDA]) + parts[0] + parts[1] + adler.to_bytes(4, "big")
+    assert zlib.decompress(stream) == data
+    sample = data[: 4 * MIB]
+    ours = len(jd.deflate_bytes(sample, 9))
+    ref = len(oracle.deflate(sample, 9))
+    assert ours <= 1.03 * ref, (ours, ref)
