@@ -265,6 +265,7 @@ struct LzSmem {
 	uint8_t  data[DATA_BYTES];
 	uint32_t spec[SEG / 32];         /* positions on the speculative paths    */
 	uint32_t fix[SEG / 32];          /* positions added by the stitching pass */
+	uint32_t take[SEG / 32];         /* positions whose match a parser arriving there takes */
 	uint32_t hist[NSYM];
 	uint32_t land[WALKERS];          /* where each walker left its block      */
 	uint32_t merge[WALKERS];
@@ -478,7 +479,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 		if ((tid & 31u) == 0) atomicAdd(&S.nomatch, nomatch);
 		__syncthreads();
 	}
-	if (prm.short3 && (prm.short3 > 1 || S.nomatch * 5u > seg_len * 2u)) {
+	if (prm.short3 && (prm.short3 > 1 || (S.nomatch * 5u > seg_len * 2u && S.nomatch * 20u < seg_len * 19u))) {   /* 40 % .. 95 %: not random data either */
 		for (uint32_t k = 0; k < PER_THREAD; k++) {
 			const uint32_t p = tid + k * LZ_THREADS;
 			if (p + 3 > seg_len || S.m[p] != 0) continue;
@@ -495,15 +496,15 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 		__syncthreads();
 	}
 
-	/* ---- per position: would a parser arriving here take the match? ---- */
+	/* ---- per position: would a parser arriving here take the match? ----
+	 * The answers also go into a bitmap (one ballot per 32 positions) that lets
+	 * the walkers below cross literal runs in one step. */
 	for (uint32_t k = 0; k < PER_THREAD; k++) {
 		const uint32_t p = tid + k * LZ_THREADS;
-		if (p >= seg_len) continue;
-		const uint32_t v = S.m[p] & ~M_TAKE;
+		const uint32_t v = p < seg_len ? (S.m[p] & ~M_TAKE) : 0u;
 		const uint32_t len = v >> 16;
-		if (len == 0) continue;
-		bool take = true;
-		if (prm.lazy && len < prm.good && p + 1 < seg_len) {
+		bool take = len != 0;
+		if (take && prm.lazy && len < prm.good && p + 1 < seg_len) {
 			const uint32_t w = S.m[p + 1] & ~M_TAKE;
 			const uint32_t nlen = w >> 16;
 			if (nlen >= len) {
@@ -516,6 +517,11 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 				}
 			}
 		}
+		const unsigned tb = __ballot_sync(JDB_FULL_MASK, take);
+		if ((tid & 31u) == 0) S.take[p >> 5] = tb;
+		/* m[p + 1] is read by the neighbouring lane in this same iteration: the flag
+		 * goes in only after every lane of the warp has read (the ballot above) --
+		 * and the mask keeps a flag set by another warp's earlier iteration harmless */
 		if (take) S.m[p] = v | M_TAKE;
 	}
 	__syncthreads();
@@ -526,10 +532,33 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 		uint32_t p = b0;
 		if (b0 < seg_len) {
 			const uint32_t lim = b1 < seg_len ? b1 : seg_len;
+			/* the TAKE bitmap word of the current 32 positions lives in a register: a
+			 * literal run inside the word is crossed in one step without touching
+			 * m[], a taken match costs one m[] load for its length; the path bits of
+			 * the word are collected in a register too (words of a block belong to
+			 * one walker: plain stores) */
+			uint32_t curw = p >> 5, tw = S.take[curw], sw = 0;
 			while (p < lim) {
-				S.spec[p >> 5] |= 1u << (p & 31);        /* words of a block belong to one walker */
-				p = next_pos(S.m, p);
+				const uint32_t w = p >> 5;
+				if (w != curw) {
+					S.spec[curw] = sw;
+					curw = w;
+					tw = S.take[w];
+					sw = 0;
+				}
+				const uint32_t sh = p & 31u;
+				const uint32_t bits = tw >> sh;
+				if (bits & 1u) {
+					sw |= 1u << sh;
+					p += (S.m[p] >> 16) & 0x1ffu;
+				} else {
+					uint32_t nlit = bits ? (uint32_t) (__ffs((int) bits) - 1) : 32u - sh;
+					if (nlit > lim - p) nlit = lim - p;
+					sw |= (nlit >= 32u ? 0xffffffffu : ((1u << nlit) - 1u)) << sh;
+					p += nlit;
+				}
 			}
+			S.spec[curw] = sw;
 		}
 		S.land[tid] = p;
 		S.merge[tid] = b0;
