@@ -246,9 +246,8 @@ chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, u
 #define DATA_BYTES   (WND + SEG + 320)             /* history + segment + look-ahead/guard */
 
 #ifdef JDB_SIMT_EMU
-/* emulator-only instrumentation (tools/emu_lz_stats.py): loop iterations per
- * thread and chain steps per position */
-extern "C" { uint32_t* jdb_emu_lz_iters = 0; uint8_t* jdb_emu_lz_steps = 0; uint64_t jdb_emu_lz_cnt[8] = {0}; }
+/* emulator-only instrumentation (tools/emu_lz_stats.py): chain steps per position */
+extern "C" { uint32_t* jdb_emu_lz_iters = 0; uint8_t* jdb_emu_lz_steps = 0; }
 #define LZ_STAT(x) x
 #else
 #define LZ_STAT(x)
