@@ -444,7 +444,7 @@ def _main(real_stdout):
             "metric": "deflate_level%d_GBps_uncompressed" % args.level, "value": round(value, 3), "unit": "GB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args, {"chunk_kib": int(os.environ.get("JDB200_CHUNK_KIB", "1024")),
+            "config": workload_config(args, {"chunk_kib": int(os.environ.get("JDB200_CHUNK_KIB", "512")),
                                              "collective": "all_gather of 24 B per rank" if world > 1 else "none"}),
             "ratio": round(n / produced, 4), "compressed_bytes_per_gpu": produced,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "inflate": inflate,

@@ -60,6 +60,7 @@
 #define ST_SRCEXH    1u
 #define ST_TGTEXH    2u
 #define ST_ERROR     3u
+#define ST_MARKER    4u            /* internal (count mode): stopped after an empty stored block */
 #define ST_REDO      0xffffffffu   /* internal: fast path hands the stream to the general decoder */
 #define E_BADCODE    2u
 #define E_BADTREE    3u
@@ -414,6 +415,7 @@ struct Stream {
 	uint8_t* dst;
 	uint64_t dst_cap;
 	int final;
+	int count_only;             /* measure a chunk: no output, stop after an empty stored block */
 	jdb_inflate_state* st;      /* NULL in batch mode */
 	/* running */
 	uint64_t out;               /* bytes written in this call */
@@ -642,9 +644,11 @@ inflate_stream(WarpMem* m, Stream& s)
 			uint64_t srcleft = s.src_len - pos, dstleft = s.dst_cap - s.out;
 			if (n > srcleft) n = srcleft;
 			if (n > dstleft) n = dstleft;
-			for (uint64_t j = lane; j < n; j += 32) put_byte(s, s.out + j, s.src[pos + j]);
+			if (!s.count_only)
+				for (uint64_t j = lane; j < n; j += 32) put_byte(s, s.out + j, s.src[pos + j]);
 			__syncwarp();
 			s.out += n;
+			const bool empty_block = stored_left == 0;
 			stored_left -= (uint32_t) n;
 			b.p += n;
 			if (stored_left) {
@@ -652,6 +656,12 @@ inflate_stream(WarpMem* m, Stream& s)
 				break;
 			}
 			phase = JDB_INF_HEADER;
+			if (s.count_only && empty_block) {
+				/* the sync / end marker that closes a chunk of our own encoder
+				 * (and of any deflate sync flush) */
+				s.status = ST_MARKER;
+				break;
+			}
 			continue;
 		}
 
@@ -794,7 +804,10 @@ inflate_stream(WarpMem* m, Stream& s)
 				__syncwarp();
 
 				/* ---- all lanes: turn the queue into bytes ---- */
-				if (nq) emit_queue(s, &m->bm, m->queue, nq, pend_len, pend_dist);
+				if (nq) {
+					if (s.count_only) s.out += qbytes;
+					else emit_queue(s, &m->bm, m->queue, nq, pend_len, pend_dist);
+				}
 				if (ev) break;
 			}
 
@@ -825,11 +838,12 @@ finish:
 	}
 	{
 		/* consumed bytes; at the end of the stream whole unread bytes go back */
-		if (s.status == ST_OK) {
+		if (s.status == ST_OK || s.status == ST_MARKER) {
 			b.p -= b.bc >> 3;
 			b.bc &= 7u;
 		}
 		s.consumed = (uint64_t) (b.p - s.src);
+		if (s.status == ST_MARKER) s.error = lastblock;       /* 1: the marker carried BFINAL */
 
 		if (s.st && s.status != ST_ERROR) {
 			jdb_inflate_state* st = s.st;
@@ -887,7 +901,7 @@ __global__ void __launch_bounds__(INF_THREADS)
 inflate_batch_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ dst_base,
                      const jdb_inflate_item* __restrict__ items, jdb_inflate_result* __restrict__ results,
                      jdb_inflate_state* states, uint32_t count, uint32_t format, uint32_t final,
-                     uint32_t* __restrict__ counter, uint32_t redo_only)
+                     uint32_t* __restrict__ counter, uint32_t redo_only, uint32_t count_only)
 {
 	JDB_DYN_SMEM(smem_raw);
 	WarpMem* m = (WarpMem*) smem_raw + jdb_warp();
@@ -908,6 +922,7 @@ inflate_batch_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__
 		s.dst = dst_base + it.dst_off;
 		s.dst_cap = it.dst_cap;
 		s.final = (int) final;
+		s.count_only = (int) count_only;
 		s.st = states ? states + idx : NULL;
 
 		uint32_t zerr = 0;
@@ -1174,6 +1189,7 @@ inflate_fast_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ 
 			s.dst_cap = __shfl_sync(JDB_FULL_MASK, (unsigned long long) dst_cap, g);
 			s.out = __shfl_sync(JDB_FULL_MASK, (unsigned long long) out, g);
 			s.st = NULL;
+			s.count_only = 0;
 			s.ring = NULL;
 			s.ring_lo = 0;
 			s.hist_avail = 0;
@@ -1275,6 +1291,86 @@ extern "C" int jdb_inflate_batch(const uint8_t* src_base, uint8_t* dst_base,
 	uint32_t cap = (uint32_t) jdb_rt_sm_count();
 	if (ctas > cap) ctas = cap;
 	JDB_LAUNCH(inflate_batch_kernel, dim3(ctas), dim3(INF_THREADS), smem, s,
-	           src_base, dst_base, items, results, states, count, format, final, counter, redo_only);
+	           src_base, dst_base, items, results, states, count, format, final, counter, redo_only, 0u);
+	return jdb_rt_check_launch("inflate_batch_kernel");
+}
+
+
+/* ---------------------------------------------------------------------------
+ * chunk discovery for the parallel decode of one large stream
+ * ------------------------------------------------------------------------- */
+
+/*
+ * Every chunk our encoder writes (and every deflate sync flush) ends in the byte
+ * aligned empty stored block .. 00 00 FF FF.  marker_scan_kernel lists the end
+ * offsets of every occurrence of those four bytes -- candidates only: the same
+ * bytes can occur inside compressed data.  The caller decodes from every
+ * candidate in count mode (jdb_inflate_measure) and keeps the chain that starts
+ * at the true stream position and hops from marker to marker.
+ */
+__global__ void __launch_bounds__(256)
+marker_scan_kernel(const uint8_t* __restrict__ src, uint64_t n, uint32_t* __restrict__ ends,
+                   uint32_t max_ends, uint32_t* __restrict__ count)
+{
+	const uint64_t stride = (uint64_t) gridDim.x * blockDim.x * 4u;
+	for (uint64_t base = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) * 4u; base + 4u <= n; base += stride) {
+		/* four candidate offsets per thread from two aligned words (src is 4-byte aligned) */
+		const uint32_t w0 = *(const uint32_t*) (src + base);
+		uint32_t w1 = 0x01010101u;
+		if (base + 8u <= n) w1 = *(const uint32_t*) (src + base + 4u);
+		else for (uint32_t k = 0; k < 4; k++)
+			if (base + 4u + k < n) w1 = (w1 & ~(0xffu << (8u * k))) | ((uint32_t) src[base + 4u + k] << (8u * k));
+#pragma unroll
+		for (uint32_t k = 0; k < 4; k++) {
+			if (base + k + 4u > n) break;
+			if (__funnelshift_r(w0, w1, 8u * k) == 0xffff0000u) {
+				const uint32_t i = atomicAdd(count, 1u);
+				if (i < max_ends) ends[i] = (uint32_t) (base + k + 4u);
+			}
+		}
+	}
+}
+
+extern "C" int jdb_marker_scan(const uint8_t* src, uint64_t n, uint32_t* ends, uint32_t max_ends,
+                               uint32_t* count, jdb_stream s)
+{
+	int r = jdb_memset_async(count, 0, sizeof(uint32_t), s);
+	if (r != JDB_OK) return r;
+	if (n < 4 || n > 0xfffffff0ull || ((uintptr_t) src & 3u)) return n < 4 ? JDB_OK : JDB_EARG;
+	uint64_t threads = (n + 3) / 4;
+	uint32_t ctas = (uint32_t) ((threads + 255) / 256);
+	const uint32_t cap = (uint32_t) jdb_rt_sm_count() * 8;
+	if (ctas > cap) ctas = cap;
+	JDB_LAUNCH(marker_scan_kernel, dim3(ctas), dim3(256), 0, s, src, n, ends, max_ends, count);
+	return jdb_rt_check_launch("marker_scan_kernel");
+}
+
+/* count mode: per item, decode from src_off without producing output until an
+ * empty stored block has been read.  results[i]: status ST_MARKER (4) with
+ * `consumed` = bytes up to and including the marker, `produced` = bytes the
+ * chunk decodes to, `error` = 1 when the marker carried BFINAL; anything else
+ * means "not a chunk of this shape". */
+extern "C" int jdb_inflate_measure(const uint8_t* src_base, const jdb_inflate_item* items,
+                                   jdb_inflate_result* results, uint32_t count,
+                                   uint32_t* counter, jdb_stream s)
+{
+	if (count == 0) return JDB_OK;
+	int r = jdb_memset_async(counter, 0, sizeof(uint32_t), s);
+	if (r != JDB_OK) return r;
+	const size_t smem = sizeof(WarpMem) * INF_WARPS;
+#ifndef JDB_SIMT_EMU
+	static int configured[64];
+	int dev = jdb_rt_get_device();
+	if (dev >= 0 && dev < 64 && !configured[dev]) {
+		cudaFuncSetAttribute(inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		configured[dev] = 1;
+	}
+#endif
+	uint32_t ctas = (count + INF_WARPS - 1) / INF_WARPS;
+	const uint32_t cap = (uint32_t) jdb_rt_sm_count();
+	if (ctas > cap) ctas = cap;
+	JDB_LAUNCH(inflate_batch_kernel, dim3(ctas), dim3(INF_THREADS), smem, s,
+	           src_base, (uint8_t*) 0, items, results, (jdb_inflate_state*) 0, count, (uint32_t) JDB_FMT_RAW, 0u,
+	           counter, 0u, 1u);
 	return jdb_rt_check_launch("inflate_batch_kernel");
 }

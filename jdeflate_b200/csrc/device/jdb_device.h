@@ -152,6 +152,14 @@ int jdb_inflate_batch(const uint8_t* src_base, uint8_t* dst_base,
                       jdb_inflate_state* states, uint32_t count, uint32_t format,
                       uint32_t final, uint32_t* counter, jdb_stream s);
 
+/* chunk discovery for the parallel decode of one large stream (inflate.cu) */
+int jdb_marker_scan(const uint8_t* src, uint64_t n, uint32_t* ends, uint32_t max_ends,
+                    uint32_t* count, jdb_stream s);
+#define JDB_INF_ST_MARKER 4u       /* jdb_inflate_measure: stopped after an empty stored block */
+int jdb_inflate_measure(const uint8_t* src_base, const jdb_inflate_item* items,
+                        jdb_inflate_result* results, uint32_t count,
+                        uint32_t* counter, jdb_stream s);
+
 /* ---- deflate pipeline stages (lz.cu, huffman.cu, pack.cu) ---------------- */
 #define JDB_SEG 16384u      /* LZ segment: positions per CTA, histogram granule */
 

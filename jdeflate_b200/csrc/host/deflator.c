@@ -27,7 +27,10 @@
 
 /* batch geometry (overridable through the environment for experiments) */
 #define DEFAULT_BATCH   ((size_t) 256 << 20)
-#define DEFAULT_CHUNK   ((size_t) 1024 << 10)   /* measured on text: +1.0 % size at 256 KiB, +0.4 % at 512 KiB, +0.1 % at 1 MiB; same speed */
+/* measured on text: +1.0 % size at 256 KiB, +0.4 % at 512 KiB, +0.1 % at 1 MiB vs the reference, same
+ * encode speed; the chunk is also the unit of the parallel decode of one stream (inflator.c), where
+ * smaller is faster -- 512 KiB is the balance */
+#define DEFAULT_CHUNK   ((size_t) 512 << 10)
 #define DEFAULT_BLOCKSEGS 4
 
 struct TDEFLTPblc {

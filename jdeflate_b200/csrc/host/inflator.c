@@ -16,12 +16,19 @@
 #include <jdeflate/b200.h>
 #include <string.h>
 #include <stddef.h>
+#include <stdlib.h>
 #include "jdb_host.h"
 #include "jdb_internal.h"
 
 #define POISON        0xDEADBEEFu
-#define INQ_BYTES     ((size_t) 32 << 20)     /* compressed bytes per launch   */
+#define INQ_BYTES     ((size_t) 32 << 20)     /* compressed bytes per launch (grows for large windows) */
+#define INQ_MAX       ((size_t) 512 << 20)
 #define OUT_BYTES     ((size_t) 64 << 20)     /* staging for host targets      */
+
+/* chunk-parallel decode of one stream (streams cut by sync markers, i.e. ours) */
+#define PAR_MAXC      65536u                  /* marker candidates per step    */
+#define PAR_MIN_BYTES ((size_t) 4 << 20)      /* queued input that makes a step worthwhile */
+#define PAR_AGAIN     0xffu                   /* internal status: a parallel step ran, not at the end */
 
 struct TINFLTPblc {
 	uint32 state;
@@ -48,6 +55,14 @@ struct TINFLTPrvt {
 	jdb_dbuf   inq;         /* unconsumed compressed bytes: [inqoff, inqoff+inqlen) */
 	size_t     inqoff;
 	size_t     inqlen;
+	size_t     inqcap;
+
+	/* chunk-parallel path: usable while the decoder sits at a block boundary with
+	 * nothing buffered (start of the stream, or right after a parallel step) */
+	uint32 par_ok;
+	uint64 par_total;       /* bytes produced so far (= device total_out) */
+	jdb_dbuf   par_dev;     /* device: candidate ends, items, results */
+	uint8*     par_host;    /* pinned mirror of the same */
 	jdb_dbuf   outbuf;
 
 	jdb_inflate_state* dstate;
@@ -139,6 +154,8 @@ inflator_reset(TInflator* state)
 	PRVT->done = 0;
 	PRVT->inqoff = 0;
 	PRVT->inqlen = 0;
+	PRVT->par_ok = 1;
+	PRVT->par_total = 0;
 
 	{
 		uint32_t* init = (uint32_t*) (PRVT->pinned + 208);
@@ -166,6 +183,8 @@ inflator_destroy(TInflator* state)
 	}
 	jdb_dbuf_release(&PRVT->inq);
 	jdb_dbuf_release(&PRVT->outbuf);
+	jdb_dbuf_release(&PRVT->par_dev);
+	jdb_pinned_free(PRVT->par_host);
 	jdb_dbuf_release(&PRVT->ckwork);
 	jdb_dev_free(PRVT->dchecks);
 	jdb_dev_free(PRVT->dstate);
@@ -203,6 +222,7 @@ inflator_setdctnr(TInflator* state, const uint8* dict, uintxx size)
 		return;
 	}
 	PRVT->used = 1;
+	PRVT->par_ok = 0;       /* history in front of the stream: sequential decoder only */
 }
 
 /* internal hooks for zstrm.c (hidden visibility) */
@@ -259,14 +279,24 @@ absorb(struct TINFLTPrvt* state)
 	if (avail == 0) {
 		return 0;
 	}
-	if (jdb_dbuf_reserve(&PRVT->inq, INQ_BYTES) != 0) {
-		/* reserve() drops the old contents: only legal while the queue is empty */
-		return -1;
-	}
 	if (PRVT->inqlen == 0) {
+		/* reserve() drops the old contents: growing is only legal while the queue
+		 * is empty.  Large windows get a large queue so that a parallel step sees
+		 * many chunks at once. */
+		size_t want = PRVT->inqcap ? PRVT->inqcap : INQ_BYTES;
+		while (want < avail && want < INQ_MAX) {
+			want *= 2;
+		}
+		if (jdb_dbuf_reserve(&PRVT->inq, want) != 0) {
+			return -1;
+		}
+		PRVT->inqcap = want;
 		PRVT->inqoff = 0;
 	}
-	if (PRVT->inqoff && PRVT->inqoff + PRVT->inqlen + avail > INQ_BYTES) {
+	if (PRVT->inq.ptr == NULL) {
+		return -1;
+	}
+	if (PRVT->inqoff && PRVT->inqoff + PRVT->inqlen + avail > PRVT->inqcap) {
 		/* compact: the tail is small (a cut header or symbol) unless the target
 		 * was the limiting side; bounce through the staging buffer */
 		if (jdb_dbuf_reserve(&PRVT->outbuf, OUT_BYTES) != 0) {
@@ -278,7 +308,7 @@ absorb(struct TINFLTPrvt* state)
 			PRVT->inqoff = 0;
 		}
 	}
-	room = INQ_BYTES - (PRVT->inqoff + PRVT->inqlen);
+	room = PRVT->inqcap - (PRVT->inqoff + PRVT->inqlen);
 	if (avail > room) {
 		avail = room;
 	}
@@ -290,6 +320,220 @@ absorb(struct TINFLTPrvt* state)
 		PBLC->source += avail;
 	}
 	return 0;
+}
+
+static int
+cmp_u32(const void* a, const void* b)
+{
+	uint32_t x = *(const uint32_t*) a, y = *(const uint32_t*) b;
+	return x < y ? -1 : x > y;
+}
+
+/* index of `v` in the sorted array a[0..n), or n */
+static uint32_t
+find_u32(const uint32_t* a, uint32_t n, uint32_t v)
+{
+	uint32_t lo = 0, hi = n;
+	while (lo < hi) {
+		uint32_t mid = lo + (hi - lo) / 2;
+		if (a[mid] < v) lo = mid + 1; else hi = mid;
+	}
+	return (lo < n && a[lo] == v) ? lo : n;
+}
+
+/*
+ * One chunk-parallel step over the queued input:
+ *   1. list every "00 00 FF FF" in the queue (marker_scan_kernel): candidate
+ *      chunk ends;
+ *   2. decode from the queue start and from every candidate in count mode
+ *      (no output) until an empty stored block is read: a real chunk reports
+ *      where it ends and how many bytes it decodes to; false candidates just
+ *      fail or lead nowhere;
+ *   3. follow the chain start -> marker -> marker ... as far as the target has
+ *      room; a running sum of the sizes places every chunk;
+ *   4. decode the chunks of the chain for real, one warp each, and check that
+ *      every one used and produced exactly what step 2 said.
+ * Nothing is assumed about who wrote the stream: a stream without such markers
+ * yields an empty chain and the sequential decoder takes over.
+ * Returns 1 when it decoded something, 0 when it does not apply, -1 on failure.
+ */
+static int
+parallel_step(struct TINFLTPrvt* state, uint8* dst, size_t cap, size_t* produced_out, int* finished)
+{
+	const size_t u32_bytes = ((size_t) PAR_MAXC + 1) * 4, rec_bytes = ((size_t) PAR_MAXC + 1) * 32;
+	const size_t total_bytes = 256 + 2 * u32_bytes + 2 * rec_bytes;
+	uint32_t* h_count;
+	uint32_t* h_ends;
+	uint32_t* h_starts;
+	jdb_inflate_item* h_items;
+	jdb_inflate_result* h_res;
+	uint8_t* d;
+	uint32_t* d_count;
+	uint32_t* d_ends;
+	jdb_inflate_item* d_items;
+	jdb_inflate_result* d_res;
+	const size_t n = PRVT->inqlen;
+	const size_t pad = PRVT->inqoff & 3u;
+	uint32_t nc, ns, i, k, nfrag;
+	uint64_t total, used;
+	int fin = 0;
+
+	*produced_out = 0;
+	*finished = 0;
+	if (n < 5 || n + pad > 0xfffffff0u) {
+		return 0;
+	}
+	if (PRVT->par_host == NULL) {
+		PRVT->par_host = jdb_pinned_alloc(total_bytes);
+		if (PRVT->par_host == NULL) {
+			return -1;
+		}
+	}
+	if (jdb_dbuf_reserve(&PRVT->par_dev, total_bytes) != 0) {
+		return -1;
+	}
+	h_count = (uint32_t*) PRVT->par_host;
+	h_ends = (uint32_t*) (PRVT->par_host + 256);
+	h_starts = (uint32_t*) (PRVT->par_host + 256 + u32_bytes);
+	h_items = (jdb_inflate_item*) (PRVT->par_host + 256 + 2 * u32_bytes);
+	h_res = (jdb_inflate_result*) (PRVT->par_host + 256 + 2 * u32_bytes + rec_bytes);
+	d = PRVT->par_dev.ptr;
+	d_count = (uint32_t*) d;
+	d_ends = (uint32_t*) (d + 256);
+	d_items = (jdb_inflate_item*) (d + 256 + 2 * u32_bytes);
+	d_res = (jdb_inflate_result*) (d + 256 + 2 * u32_bytes + rec_bytes);
+
+	/* 1. candidates (the scan wants a 4-byte aligned start: begin up to 3 bytes early) */
+	if (jdb_marker_scan(PRVT->inq.ptr + PRVT->inqoff - pad, n + pad, d_ends, PAR_MAXC, d_count, PRVT->stream) != JDB_OK ||
+	    jdb_copy_async(h_count, d_count, 4, PRVT->stream) != JDB_OK ||
+	    jdb_stream_sync(PRVT->stream) != JDB_OK) {
+		return -1;
+	}
+	nc = h_count[0];
+	if (nc == 0 || nc > PAR_MAXC) {
+		return 0;
+	}
+	if (jdb_copy_async(h_ends, d_ends, (size_t) nc * 4, PRVT->stream) != JDB_OK ||
+	    jdb_stream_sync(PRVT->stream) != JDB_OK) {
+		return -1;
+	}
+	qsort(h_ends, nc, 4, cmp_u32);
+
+	/* 2. measure from the start and from every candidate that has input after it
+	 * (offsets from here on are relative to the first queued byte) */
+	ns = 0;
+	h_starts[ns++] = 0;
+	for (i = 0; i < nc; i++) {
+		if (h_ends[i] > pad && h_ends[i] - pad < n) {
+			h_starts[ns++] = (uint32_t) (h_ends[i] - pad);
+		}
+	}
+	for (i = 0; i < ns; i++) {
+		h_items[i].src_off = PRVT->inqoff + h_starts[i];
+		h_items[i].dst_off = 0;
+		h_items[i].src_len = n - h_starts[i];
+		h_items[i].dst_cap = (uint64_t) 1 << 62;
+	}
+	if (jdb_copy_async(d_items, h_items, (size_t) ns * sizeof(*h_items), PRVT->stream) != JDB_OK ||
+	    jdb_inflate_measure(PRVT->inq.ptr, d_items, d_res, ns, D_COUNTER(PRVT), PRVT->stream) != JDB_OK ||
+	    jdb_copy_async(h_res, d_res, (size_t) ns * sizeof(*h_res), PRVT->stream) != JDB_OK ||
+	    jdb_stream_sync(PRVT->stream) != JDB_OK) {
+		return -1;
+	}
+
+	/* 3. the chain of real chunks, as far as the target has room; the items of
+	 * the real decode are written over the measured ones as we go (slot nfrag
+	 * is never ahead of the slot k being read) */
+	total = 0;
+	used = 0;
+	nfrag = 0;
+	k = 0;
+	while (k < ns) {
+		const jdb_inflate_result r = h_res[k];
+		const uint32_t start = h_starts[k];
+		uint64_t next;
+		if (r.status != JDB_INF_ST_MARKER || r.consumed == 0 || r.consumed > n - start) {
+			break;
+		}
+		if (total + r.produced > cap) {
+			break;
+		}
+		h_items[nfrag].src_off = PRVT->inqoff + start;
+		h_items[nfrag].dst_off = total;
+		h_items[nfrag].src_len = r.consumed;
+		h_items[nfrag].dst_cap = r.produced;
+		nfrag++;
+		total += r.produced;
+		used = start + r.consumed;
+		if (r.error) {
+			fin = 1;                    /* the marker carried BFINAL: end of the stream */
+			break;
+		}
+		next = start + r.consumed;
+		if (next >= n) {
+			break;
+		}
+		k = find_u32(h_starts + nfrag, ns - nfrag, (uint32_t) next);
+		if (k == ns - nfrag) {
+			break;
+		}
+		k += nfrag;
+	}
+	if (nfrag == 0) {
+		return 0;
+	}
+
+	/* 4. the real decode */
+	if (jdb_copy_async(d_items, h_items, (size_t) nfrag * sizeof(*h_items), PRVT->stream) != JDB_OK ||
+	    jdb_inflate_batch(PRVT->inq.ptr, dst, d_items, d_res, NULL, nfrag, JDB_FMT_RAW, 0,
+	                      D_COUNTER(PRVT), PRVT->stream) != JDB_OK ||
+	    jdb_copy_async(h_res, d_res, (size_t) nfrag * sizeof(*h_res), PRVT->stream) != JDB_OK ||
+	    jdb_stream_sync(PRVT->stream) != JDB_OK) {
+		return -1;
+	}
+	for (i = 0; i < nfrag; i++) {
+		if (h_res[i].status > INFLT_SRCEXHSTD || h_res[i].produced != h_items[i].dst_cap ||
+		    h_res[i].consumed != h_items[i].src_len) {
+			return -1;
+		}
+	}
+
+	/* the sequential decoder may have to go on from here: leave its state at the
+	 * block boundary after the last chunk, with the newest 32 KiB as history */
+	{
+		const uint64_t newtotal = PRVT->par_total + total;
+		uint64_t h = total < JDB_INFLATE_HISTORY ? total : JDB_INFLATE_HISTORY;
+		uint64_t first = newtotal - h;                       /* absolute position of the oldest byte copied */
+		uint64_t head = JDB_INFLATE_HISTORY - (first & (JDB_INFLATE_HISTORY - 1));
+		uint64_t* hw = (uint64_t*) (PRVT->pinned + 128);
+		uint32_t* hw32 = (uint32_t*) (PRVT->pinned + 128 + 24);
+		if (head > h) {
+			head = h;
+		}
+		if (jdb_copy_async(PRVT->dstate->history + (first & (JDB_INFLATE_HISTORY - 1)), dst + total - h, (size_t) head, PRVT->stream) != JDB_OK ||
+		    jdb_copy_async(PRVT->dstate->history, dst + total - h + head, (size_t) (h - head), PRVT->stream) != JDB_OK) {
+			return -1;
+		}
+		hw[0] = 0;                                           /* bitbuf */
+		hw[1] = newtotal;                                    /* total_out */
+		hw[2] = newtotal < JDB_INFLATE_HISTORY ? newtotal : JDB_INFLATE_HISTORY;   /* hist_avail */
+		hw32[0] = 0;                                         /* bitcnt */
+		hw32[1] = JDB_INF_HEADER;                            /* phase */
+		hw32[2] = (uint32_t) fin;                            /* lastblock */
+		hw32[3] = 0;                                         /* stored_left */
+		hw32[4] = 0;                                         /* pend_len */
+		hw32[5] = 0;                                         /* pend_dist */
+		if (jdb_copy_async(PRVT->dstate, hw, offsetof(jdb_inflate_state, lit), PRVT->stream) != JDB_OK ||
+		    jdb_stream_sync(PRVT->stream) != JDB_OK) {
+			return -1;
+		}
+		PRVT->par_total = newtotal;
+	}
+	PRVT->inqoff += (size_t) used;
+	PRVT->inqlen -= (size_t) used;
+	*produced_out = (size_t) total;
+	*finished = fin;
+	return 1;
 }
 
 eINFLTResult
@@ -353,7 +597,35 @@ inflator_inflate(TInflator* state, uint32 final)
 				poison(PRVT, INFLT_EOOM);
 				return INFLT_ERROR;
 			}
+			PRVT->inqcap = INQ_BYTES;
 		}
+
+		/* a stream cut into chunks by sync markers (ours) is decoded chunk-parallel
+		 * while the decoder sits at a block boundary */
+		if (PRVT->par_ok &&
+		    (PRVT->inqlen >= PAR_MIN_BYTES || (PBLC->finalinput && absorbed_all && PRVT->inqlen >= ((size_t) 256 << 10)))) {
+			size_t made = 0;
+			int fin = 0;
+			int pr = parallel_step(PRVT, dst, cap, &made, &fin);
+			if (pr < 0) {
+				poison(PRVT, INFLT_EBADSTATE);
+				return INFLT_ERROR;
+			}
+			if (pr > 0) {
+				/* not finished: go round again -- more chunks, or the sequential decoder
+				 * for what follows (it alone decides between "target full", "need input"
+				 * and "stream ended") */
+				res->status = fin ? INFLT_OK : PAR_AGAIN;
+				res->error = 0;
+				res->consumed = 0;              /* the queue was advanced by the step itself */
+				res->produced = made;
+				goto L_DELIVER;
+			}
+			/* no chain of chunks here: the sequential decoder owns the stream from now on */
+			PRVT->par_ok = 0;
+		}
+		PRVT->par_ok = 0;
+
 		if (jdb_copy_async(D_ITEM(PRVT), item, sizeof(*item), PRVT->stream) != JDB_OK ||
 		    jdb_inflate_batch(PRVT->inq.ptr, dst, D_ITEM(PRVT), D_RESULT(PRVT), PRVT->dstate, 1,
 		                      JDB_FMT_RAW, (uint32_t) (PBLC->finalinput && absorbed_all),
@@ -364,6 +636,7 @@ inflator_inflate(TInflator* state, uint32 final)
 			return INFLT_ERROR;
 		}
 
+L_DELIVER:
 		/* account for what the device used */
 		PRVT->inqoff += (size_t) res->consumed;
 		PRVT->inqlen -= (size_t) res->consumed;
@@ -405,6 +678,8 @@ inflator_inflate(TInflator* state, uint32 final)
 				PBLC->error = res->error ? res->error : INFLT_EBADSTATE;
 				PBLC->state = POISON;
 				return INFLT_ERROR;
+			case PAR_AGAIN:
+				continue;
 			case INFLT_TGTEXHSTD:
 				if (PBLC->target == PBLC->tend) {
 					return (eINFLTResult) (PBLC->status = INFLT_TGTEXHSTD);

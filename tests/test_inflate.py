@@ -164,3 +164,49 @@ def test_lane_parallel_batch_path_matches_general_decoder(lib, corpus, monkeypat
     fast = run()
     assert fast == general
     assert general[0][0] == recs[0] and general[-1][0] == recs[-1]
+
+
+def _flushed_stream(data, piece, mode):
+    """Raw deflate by zlib with a flush of `mode` after every `piece` bytes."""
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    out = bytearray()
+    for off in range(0, len(data), piece):
+        out += co.compress(data[off:off + piece])
+        out += co.flush(mode)
+    out += co.flush(zlib.Z_FINISH)
+    return bytes(out)
+
+
+def test_chunk_parallel_decode_of_marker_cut_streams(lib, oracle, corpus, monkeypatch):
+    """Streams cut into independent chunks by sync markers (ours; zlib's Z_FULL_FLUSH) are decoded
+    chunk-parallel inside the plain inflator; the result -- bytes, status,
+    consumed input -- must be what the sequential decoder gives, for every shape of target window,
+    and streams that merely LOOK chunked (Z_SYNC_FLUSH: matches cross the markers; marker bytes
+    inside stored data) must fall back cleanly."""
+    monkeypatch.setenv("JDB200_CHUNK_KIB", "64")
+    d = corpus.fill(5, 1200000, offset=(4 << 20) - 500000)          # TEXT then BINARY
+    ours = lib.deflate_bytes(d, 6)
+    assert ours.count(b"\x00\x00\xff\xff") >= 18
+    full = _flushed_stream(d, 50000, zlib.Z_FULL_FLUSH)
+    sync = _flushed_stream(d, 50000, zlib.Z_SYNC_FLUSH)
+    noise = b"\x00\x00\xff\xff" * 2000 + corpus.fill(3, 300000)       # marker bytes as payload
+    stored = zlib_raw(noise, 0)
+    for name, z, want in (("ours", ours, d), ("full_flush", full, d), ("sync_flush", sync, d), ("stored_noise", stored, noise)):
+        assert len(z) >= 256 << 10, name
+        for window in (None, 1 << 20, 100000, 65536 + 7):
+            st, err, out, used = lib.inflate_bytes(z + b"tail", len(want), window=window)
+            assert (st, err, used) == (api.OK, 0, len(z)), (name, window)
+            assert out == want, (name, window)
+        # not final, input ends in the middle of a chunk: everything decodable comes out, then SRCEXHSTD
+        cut = len(z) * 2 // 3
+        st, err, out, used = lib.inflate_bytes(z[:cut], len(want), final=False)
+        ost = oracle.inflate(z[:cut], len(want), final=False)
+        assert (st, err) == (api.SRCEXHSTD, 0) and out == ost[2], name
+    # damage inside a chunk of our own stream: the error of the sequential decoder
+    bad = bytearray(ours)
+    bad[len(bad) // 2] ^= 0x5a
+    got = lib.inflate_bytes(bytes(bad), len(d))
+    exp = oracle.inflate(bytes(bad), len(d))
+    assert (got[0], got[1]) == (exp[0], exp[1])
+    if exp[0] == api.OK:
+        assert got[2] == exp[2]
