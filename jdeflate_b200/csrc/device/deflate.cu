@@ -28,7 +28,7 @@
 #include "deflate.cuh"
 
 extern "C" int jdb_huffman_blocks(const uint32_t*, const uint32_t*, uint64_t, uint32_t, uint32_t, uint32_t,
-                                  uint32_t, uint32_t, void*, jdb_stream);
+                                  uint32_t, uint32_t, uint32_t, void*, jdb_stream);
 extern "C" size_t jdb_blockinfo_bytes(void);
 extern "C" int jdb_pack_layout(void*, void*, uint32_t, uint32_t, uint32_t*, uint64_t, uint64_t*, jdb_stream);
 extern "C" int jdb_pack_blocks(const uint8_t*, const uint32_t*, const uint32_t*, const void*, const void*,
@@ -115,11 +115,11 @@ extern "C" int jdb_deflate_run(const uint8_t* in, uint64_t n, const jdb_deflate_
 		r = jdb_lz_chain(in, n, cfg->chunk_bytes, range, prev, s);
 		if (r != JDB_OK) return r;
 		r = jdb_lz_parse(in, n, cfg->chunk_bytes, prev, cfg->good, cfg->nice, cfg->chain, cfg->lazy,
-		                 tok, seg_ntok, seg_hist, s);
+		                 cfg->dict_region / SEG, cfg->dict_pad, tok, seg_ntok, seg_hist, s);
 		if (r != JDB_OK) return r;
 	}
 	r = jdb_huffman_blocks(seg_ntok, seg_hist, n, cfg->chunk_bytes, cfg->block_segs, L.nblocks,
-	                       cfg->level, cfg->fixedonly, blocks, s);
+	                       cfg->level, cfg->fixedonly, cfg->dict_region / (cfg->block_segs * SEG), blocks, s);
 	if (r != JDB_OK) return r;
 	r = jdb_pack_layout(blocks, chunks, L.nchunks, L.bpc, outw, L.out_cap / 4, total, s);
 	if (r != JDB_OK) return r;

@@ -196,7 +196,7 @@ struct HdrWriter {
 __global__ void __launch_bounds__(HF_THREADS)
 huffman_kernel(const uint32_t* __restrict__ seg_ntok, const uint32_t* __restrict__ seg_hist,
                uint64_t n, uint32_t chunk_bytes, uint32_t block_segs, uint32_t nblocks,
-               uint32_t level, uint32_t fixedonly, BlockInfo* __restrict__ blocks)
+               uint32_t level, uint32_t fixedonly, uint32_t skip_blocks, BlockInfo* __restrict__ blocks)
 {
 	__shared__ HfSmem smem[HF_WARPS];
 	HfSmem& S = smem[jdb_warp()];
@@ -214,6 +214,7 @@ huffman_kernel(const uint32_t* __restrict__ seg_ntok, const uint32_t* __restrict
 	const uint32_t s0 = k * block_segs;
 	uint32_t ns = s0 < csegs ? csegs - s0 : 0;
 	if (ns > block_segs) ns = block_segs;
+	if (b < skip_blocks) ns = 0;                 /* preset dictionary: history only, no block */
 	const uint32_t gseg0 = chunk * segs_per_chunk + s0;
 	const uint64_t in_off = chunk0 + (uint64_t) s0 * SEG;
 	uint64_t in_end = in_off + (uint64_t) ns * SEG;
@@ -386,11 +387,11 @@ huffman_kernel(const uint32_t* __restrict__ seg_ntok, const uint32_t* __restrict
 
 extern "C" int jdb_huffman_blocks(const uint32_t* seg_ntok, const uint32_t* seg_hist, uint64_t n,
                                   uint32_t chunk_bytes, uint32_t block_segs, uint32_t nblocks,
-                                  uint32_t level, uint32_t fixedonly, void* blocks, jdb_stream s)
+                                  uint32_t level, uint32_t fixedonly, uint32_t skip_blocks, void* blocks, jdb_stream s)
 {
 	if (nblocks == 0) return JDB_OK;
 	JDB_LAUNCH(huffman_kernel, dim3((nblocks + HF_WARPS - 1) / HF_WARPS), dim3(HF_THREADS), 0, s,
-	           seg_ntok, seg_hist, n, chunk_bytes, block_segs, nblocks, level, fixedonly, (BlockInfo*) blocks);
+	           seg_ntok, seg_hist, n, chunk_bytes, block_segs, nblocks, level, fixedonly, skip_blocks, (BlockInfo*) blocks);
 	return jdb_rt_check_launch("huffman_kernel");
 }
 

@@ -172,12 +172,13 @@ int jdb_lz_chain(const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint32_t r
  * in seg_ntok[k], the 320-bin symbol histogram in seg_hist[k*320 ...) */
 int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes, const uint16_t* prev,
                  uint32_t good, uint32_t nice, uint32_t chain, uint32_t lazy,
+                 uint32_t skip_segs, uint32_t hist_min,
                  uint32_t* tok, uint32_t* seg_ntok, uint32_t* seg_hist, jdb_stream s);
 
 /* per block Huffman code construction + block type choice */
 int jdb_huffman_blocks(const uint32_t* seg_ntok, const uint32_t* seg_hist, uint64_t n,
                        uint32_t chunk_bytes, uint32_t block_segs, uint32_t nblocks,
-                       uint32_t level, uint32_t fixedonly, void* blocks, jdb_stream s);
+                       uint32_t level, uint32_t fixedonly, uint32_t skip_blocks, void* blocks, jdb_stream s);
 
 /* ---- whole pipeline (deflate.cu) ---------------------------------------- */
 typedef struct jdb_deflate_cfg {
@@ -188,6 +189,11 @@ typedef struct jdb_deflate_cfg {
 	uint32_t block_segs;     /* segments per DEFLATE block, 1..16                   */
 	uint32_t chain_range;    /* positions per chain-building warp (0: whole chunk)  */
 	uint32_t final;          /* last chunk closes the stream (BFINAL = 1)           */
+	/* preset dictionary (first batch of a stream only): the batch starts with
+	 * `dict_region` bytes -- zero padding, then the dictionary -- that are history
+	 * for the first chunk but produce no output; a multiple of the block size */
+	uint32_t dict_region;
+	uint32_t dict_pad;       /* bytes of padding in front of the dictionary          */
 } jdb_deflate_cfg;
 
 size_t jdb_deflate_workspace_bytes(uint64_t n, const jdb_deflate_cfg* cfg);

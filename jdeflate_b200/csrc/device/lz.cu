@@ -256,6 +256,8 @@ extern "C" { uint32_t* jdb_emu_lz_iters = 0; uint8_t* jdb_emu_lz_steps = 0; }
 struct LzParams {
 	uint32_t good, nice, chain, lazy;
 	uint32_t short3;                 /* probe short distances for 3-byte matches */
+	uint32_t skip_segs;              /* leading segments that are preset dictionary: history only */
+	uint32_t hist_min;               /* first byte of the batch a match of chunk 0 may reach (dictionary start) */
 };
 
 struct LzSmem {
@@ -295,6 +297,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 	LzSmem& S = *(LzSmem*) smem_raw;
 	const uint32_t tid = threadIdx.x;
 	const uint32_t seg = blockIdx.x;
+	if (seg < prm.skip_segs) return;             /* dictionary: nothing to parse, nothing to emit */
 
 	const uint64_t seg0 = (uint64_t) seg * SEG;
 	const uint64_t chunk0 = seg0 / chunk_bytes * chunk_bytes;
@@ -356,6 +359,8 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 	 * lanes active instead of diverging on every step. */
 	{
 		enum { M_FETCH = 0, M_WALK = 1, M_COMPARE = 2, M_DONE = 3 };
+		/* with a preset dictionary the padding in front of it is not history */
+		const uint32_t first_valid = (chunk0 == 0 && prm.hist_min > hist0) ? (uint32_t) (prm.hist_min - hist0) : 0u;
 		const uint32_t nice = prm.nice;
 		const uint32_t lane = tid & 31u;
 		uint32_t mode = M_FETCH;
@@ -449,6 +454,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 						if (maxlen > MAXLEN) maxlen = MAXLEN;
 						j = hoff + p;
 						jmin = j > WND - 1 ? j - (WND - 1) : 0;
+						if (jmin < first_valid) jmin = first_valid;
 						dmax = j - jmin;
 						best = MINLEN - 1; bestd = 0; cur = j; steps = prm.chain;
 						cb = S.data[j + best];
@@ -478,7 +484,8 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 		if ((tid & 31u) == 0) atomicAdd(&S.nomatch, nomatch);
 		__syncthreads();
 	}
-	if (prm.short3 && (prm.short3 > 1 || (S.nomatch * 5u > seg_len * 2u && S.nomatch * 20u < seg_len * 19u))) {   /* 40 % .. 95 %: not random data either */
+	if (prm.short3 && (prm.short3 > 1 || (S.nomatch * 5u > seg_len * 2u && S.nomatch * 20u < seg_len * 19u))) {
+		const uint32_t sv = (chunk0 == 0 && prm.hist_min > hist0) ? (uint32_t) (prm.hist_min - hist0) : 0u;   /* 40 % .. 95 %: not random data either */
 		for (uint32_t k = 0; k < PER_THREAD; k++) {
 			const uint32_t p = tid + k * LZ_THREADS;
 			if (p + 3 > seg_len || S.m[p] != 0) continue;
@@ -488,7 +495,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 #pragma unroll
 			for (int u = 0; u < 12; u++) {
 				const uint32_t d = c_short_dist[u];
-				if (!found && d <= j && (jdb_ld32u(S.data, j - d) & 0xffffffu) == w) found = d;
+				if (!found && d <= j && j - d >= sv && (jdb_ld32u(S.data, j - d) & 0xffffffu) == w) found = d;
 			}
 			if (found) S.m[p] = (3u << 16) | found;
 		}
@@ -660,6 +667,7 @@ extern "C" int jdb_lz_chain(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
 
 extern "C" int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes, const uint16_t* prev,
                             uint32_t good, uint32_t nice, uint32_t chain, uint32_t lazy,
+                            uint32_t skip_segs, uint32_t hist_min,
                             uint32_t* tok, uint32_t* seg_ntok, uint32_t* seg_hist, jdb_stream s)
 {
 	if (n == 0) return JDB_OK;
@@ -674,6 +682,7 @@ extern "C" int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
 #endif
 	LzParams prm;
 	prm.good = good; prm.nice = nice; prm.chain = chain; prm.lazy = lazy;
+	prm.skip_segs = skip_segs; prm.hist_min = hist_min;
 	prm.short3 = getenv("JDB_LZ_SHORT3") ? (uint32_t) atoi(getenv("JDB_LZ_SHORT3")) : 1u;
 	const uint64_t nseg = (n + SEG - 1) / SEG;
 	JDB_LAUNCH(lz_kernel, dim3((unsigned) nseg), dim3(LZ_THREADS), smem, s,

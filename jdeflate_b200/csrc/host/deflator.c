@@ -72,6 +72,8 @@ struct TDEFLTPrvt {
 	uint32 used;
 	uint32 closed;          /* the marker of the current request has been written */
 	uint32 closing;         /* ... has been launched                               */
+	uint32 dict_region;     /* preset dictionary staged in front of the first batch (bytes, 0: none) */
+	uint32 dict_pad;
 
 	jdb_deflate_cfg cfg;
 	size_t batchcap;
@@ -92,6 +94,8 @@ struct TDEFLTPrvt {
 	uint32_t* hchecks;      /* pinned mirror              */
 	jdb_dbuf  ckwork;
 };
+
+static int stage_reserve(struct TDEFLTPrvt* state, struct jdb_slot* sl, size_t want);
 
 typedef char jdb_deflator_layout_check[(sizeof(struct TDeflator) == sizeof(struct TDEFLTPblc)) ? 1 : -1];
 
@@ -200,6 +204,8 @@ deflator_reset(TDeflator* state)
 	PRVT->used = 0;
 	PRVT->closed = 0;
 	PRVT->closing = 0;
+	PRVT->dict_region = 0;
+	PRVT->dict_pad = 0;
 	if (PRVT->stream) {
 		/* nothing of an abandoned request may still be running */
 		jdb_stream_sync(PRVT->stream);
@@ -260,17 +266,55 @@ deflator_destroy(TDeflator* state)
 void
 deflator_setdctnr(TDeflator* state, const uint8* dict, uintxx size)
 {
+	struct jdb_slot* sl;
+	size_t blockbytes, region, pad;
 	CTB_ASSERT(state && dict && size);
-	(void) dict;
-	(void) size;
-	/* the reference accepts a dictionary only before the first deflate call
-	 * (src/deflator.c:2116-2120).  Preset dictionaries are row f2 ("next") of
-	 * the scope table and not implemented yet: refuse loudly instead of
-	 * silently producing a stream the peer cannot decode. */
-	if (PBLC->error == 0) {
-		PBLC->error = DEFLT_EINCORRECTUSE;
+
+	if (PBLC->state == POISON) {
+		return;
 	}
-	PBLC->state = POISON;
+	/* only before the first deflate call, and only once (src/deflator.c:2116-2120) */
+	if (PRVT->used || PRVT->dict_region) {
+		if (PBLC->error == 0) {
+			PBLC->error = DEFLT_EINCORRECTUSE;
+		}
+		PBLC->state = POISON;
+		return;
+	}
+	if (PRVT->level == 0) {
+		return;                 /* stored blocks never reference it (the reference: no-op at level 0) */
+	}
+	if (jdb_rt_init() != JDB_OK) {
+		return;
+	}
+	/* the last 32 KiB are what a match can reach */
+	if (size > 32768) {
+		dict += size - 32768;
+		size = 32768;
+	}
+	/* The dictionary is history for the FIRST chunk only (chunks are independent): it is
+	 * staged in front of the first batch as whole DEFLATE-block slots -- zero padding, then
+	 * the dictionary -- which the kernels use as match source but never emit. */
+	blockbytes = (size_t) PRVT->cfg.block_segs * JDB_SEG;
+	region = (size + blockbytes - 1) / blockbytes * blockbytes;
+	pad = region - size;
+	if ((size_t) PRVT->cfg.chunk_bytes < region + blockbytes || PRVT->batchcap < region + blockbytes) {
+		return;                 /* chunk too small to hold dictionary + data: compress without it (still a valid stream) */
+	}
+	sl = &PRVT->slot[PRVT->fil];
+	if (stage_reserve(PRVT, sl, region + blockbytes) != 0 ||
+	    jdb_memset_async(sl->stage.ptr, 0, pad, PRVT->cstream) != JDB_OK ||
+	    jdb_copy_async(sl->stage.ptr + pad, dict, size, PRVT->cstream) != JDB_OK ||
+	    jdb_stream_sync(PRVT->cstream) != JDB_OK) {
+		if (PBLC->error == 0) {
+			PBLC->error = DEFLT_EOOM;
+		}
+		PBLC->state = POISON;
+		return;
+	}
+	sl->stagelen = region;
+	PRVT->dict_region = (uint32) region;
+	PRVT->dict_pad = (uint32) pad;
 }
 
 /* internal hooks for zstrm.c (hidden visibility) */
@@ -324,16 +368,27 @@ launch_batch(struct TDEFLTPrvt* state, int k, const uint8* in, size_t n, int clo
 	uint8_t* out;
 	uint64_t* dtotal;
 
+	size_t skip = 0;
+
 	PRVT->cfg.final = (uint32_t) (closes && PBLC->flush == DEFLT_END);
+	PRVT->cfg.dict_region = 0;
+	PRVT->cfg.dict_pad = 0;
+	if (PRVT->dict_region && !inplace && n >= PRVT->dict_region) {
+		/* first batch of a stream with a preset dictionary */
+		PRVT->cfg.dict_region = PRVT->dict_region;
+		PRVT->cfg.dict_pad = PRVT->dict_pad;
+		skip = PRVT->dict_region;
+		PRVT->dict_region = 0;
+	}
 	need = jdb_deflate_workspace_bytes(n, &PRVT->cfg);
 	if (need == 0 || jdb_dbuf_reserve(&sl->work, need) != 0) {
 		return -1;
 	}
-	if (PRVT->checks && n) {
+	if (PRVT->checks && n > skip) {
 		if (jdb_dbuf_reserve(&PRVT->ckwork, jdb_checksum_workspace_bytes()) != 0) {
 			return -1;
 		}
-		if (jdb_checksum(in, n, PRVT->checks, PRVT->dchecks, PRVT->dchecks + 1,
+		if (jdb_checksum(in + skip, n - skip, PRVT->checks, PRVT->dchecks, PRVT->dchecks + 1,
 		                 PRVT->ckwork.ptr, PRVT->stream) != JDB_OK) {
 			return -1;
 		}

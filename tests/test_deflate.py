@@ -162,3 +162,45 @@ def test_multi_batch_pipeline(lib, oracle, corpus, monkeypatch):
     finally:
         de.close()
     check_stream(oracle, za + zb, d)
+
+
+def test_preset_dictionary(lib, corpus):
+    """deflator_setdctnr (reference src/deflator.c:2106-2167): the stream needs the same dictionary
+    to decode, uses it (smaller than without), and is read back by zlib and by our inflator."""
+    dct = corpus.fill(4, 20000, offset=1)
+    for n in (300, 5000, 200000):
+        d = corpus.fill(4, n, offset=9)                  # same kind of JSON: shares a lot with the dictionary
+        for level in (1, 6, 9):
+            de = lib.deflator(level)
+            try:
+                de.setdctnr(dct)
+                z = de.run(d)
+            finally:
+                de.close()
+            assert zlib.decompressobj(-15, zdict=dct).decompress(z) == d, (n, level)
+            plain = lib.deflate_bytes(d, level)
+            assert len(z) < len(plain) or n > 100000, (n, level, len(z), len(plain))
+            s = lib.inflator()
+            try:
+                s.setdctnr(dct)
+                st, err, out, used = s.run(z, n)
+                assert (st, err, out, used) == (api.OK, 0, d, len(z))
+            finally:
+                s.close()
+            if n <= 5000:
+                with pytest.raises(zlib.error):
+                    zlib.decompress(z, -15)              # really depends on the dictionary
+    # after the first call it is a usage error; at level 0 it is ignored
+    de = lib.deflator(6)
+    try:
+        de.run(b"abc", flush=api.DEFLT_FLUSH)
+        de.setdctnr(dct)
+        assert de.state == api.POISON and de.error == api.DEFLT_EINCORRECTUSE
+    finally:
+        de.close()
+    de = lib.deflator(0)
+    try:
+        de.setdctnr(dct)
+        assert zlib.decompress(de.run(b"hello"), -15) == b"hello"
+    finally:
+        de.close()

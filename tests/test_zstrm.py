@@ -210,3 +210,33 @@ def test_cross_decode_with_compiled_reference(lib, ref, corpus):
     rcomp, _ = compress(ref, d, api.ZSTRM_GZIP, piece=10000)
     back, err, info = decompress(lib, rcomp)
     assert (back, err) == (d, 0)
+
+
+def test_zlib_preset_dictionary_deflate(lib, corpus):
+    """zstrm_setdctnr on the compress side: FDICT + DICTID in the zlib header (src/zstrm.c:1033-1050)."""
+    dct = corpus.fill(0, 12000, offset=5)
+    d = dct[2000:6000] + corpus.fill(0, 30000, offset=77)
+    out = bytearray()
+    z = lib.zstrm(api.ZSTRM_DEFLATE | api.ZSTRM_ZLIB, 6)
+    try:
+        z.settargetfn(lambda b: (out.extend(b), len(b))[1])
+        z.setdctnr(dct)
+        assert z.error == 0 and z.s.dictid == zlib.adler32(dct)
+        assert z.deflate(d) == len(d)
+        z.flush(1)
+        assert z.error == 0
+    finally:
+        z.close()
+    comp = bytes(out)
+    assert comp[1] & 0x20 and comp[2:6] == zlib.adler32(dct).to_bytes(4, "big")
+    do = zlib.decompressobj(zdict=dct)
+    assert do.decompress(comp) == d
+    zi = lib.zstrm(api.ZSTRM_INFLATE)
+    try:
+        zi.setsource(comp)
+        assert zi.state == 2
+        zi.setdctnr(dct)
+        got = zi.inflate(len(d) + 10)
+        assert got == d and zi.error == 0
+    finally:
+        zi.close()

@@ -6,7 +6,7 @@ from support import Corpus, KIND_NAMES, Oracle
 
 lib = C.CDLL(str(R / "tests/simt/_build/libjdeflate_emu.so"))
 class Cfg(C.Structure):
-    _fields_ = [(k, C.c_uint32) for k in ("level","fixedonly","good","nice","chain","lazy","chunk_bytes","block_segs","chain_range","final")]
+    _fields_ = [(k, C.c_uint32) for k in ("level","fixedonly","good","nice","chain","lazy","chunk_bytes","block_segs","chain_range","final","dict_region","dict_pad")]
 lib.jdb_dev_alloc.restype = C.c_void_p; lib.jdb_dev_alloc.argtypes = [C.c_size_t]
 lib.jdb_dev_free.argtypes = [C.c_void_p]
 lib.jdb_deflate_workspace_bytes.restype = C.c_size_t; lib.jdb_deflate_workspace_bytes.argtypes = [C.c_uint64, C.POINTER(Cfg)]
@@ -15,7 +15,7 @@ PARAMS = {1:(8,4,2,0),2:(8,8,8,0),3:(8,16,16,0),4:(8,32,32,0),5:(8,64,128,0),6:(
 
 def deflate(data, level=6, chunk=262144, block_segs=4, final=1, fixedonly=0, chain_range=0):
     g,n_,c,l = PARAMS.get(level,(0,0,0,0))
-    cfg = Cfg(level, fixedonly, g, n_, c, l, chunk, block_segs, chain_range, final)
+    cfg = Cfg(level, fixedonly, g, n_, c, l, chunk, block_segs, chain_range, final, 0, 0)
     n = len(data)
     wb = lib.jdb_deflate_workspace_bytes(n, C.byref(cfg)); assert wb
     work = lib.jdb_dev_alloc(wb); din = lib.jdb_dev_alloc(n + 64); C.memmove(din, data, n)

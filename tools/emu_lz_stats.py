@@ -8,7 +8,7 @@ from jdeflate_b200.build import build_emu
 lib = C.CDLL(str(build_emu()))
 lib.jdb_dev_alloc.restype = C.c_void_p; lib.jdb_dev_alloc.argtypes = [C.c_size_t]
 lib.jdb_lz_chain.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
-lib.jdb_lz_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p] + [C.c_uint32] * 4 + [C.c_void_p] * 4
+lib.jdb_lz_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p] + [C.c_uint32] * 6 + [C.c_void_p] * 4
 SEG = 16384
 c = Corpus()
 n = 1 << 20
@@ -23,7 +23,7 @@ for kind in (0, 1, 2, 4):
         C.c_void_p.in_dll(lib, "jdb_emu_lz_iters").value = iters.ctypes.data
         C.c_void_p.in_dll(lib, "jdb_emu_lz_steps").value = steps.ctypes.data
         assert lib.jdb_lz_chain(din, n, 262144, 262144, prev, None) == 0
-        assert lib.jdb_lz_parse(din, n, 262144, prev, good, nice, chain, lazy, tok, ntok, hist, None) == 0
+        assert lib.jdb_lz_parse(din, n, 262144, prev, good, nice, chain, lazy, 0, 0, tok, ntok, hist, None) == 0
         st = steps.reshape(nseg, 16, 32, 32)          # seg, k, warp, lane  (p = tid + k*1024)
         sum_of_max = st.max(axis=3).sum(axis=1)       # nested loops: per warp sum over k of max over lanes
         print(KIND_NAMES[kind], "chain", chain, "chain steps per position: mean %.2f" % steps.mean(), "p50", np.percentile(steps, 50), "p90", np.percentile(steps, 90),
