@@ -679,6 +679,13 @@ L_DELIVER:
 				PBLC->state = POISON;
 				return INFLT_ERROR;
 			case PAR_AGAIN:
+				/* a streaming caller: the queue holds only the beginning of the next
+				 * chunk and more input is coming -- ask for it and stay on the parallel
+				 * path instead of handing the stream to the sequential decoder */
+				if (absorbed_all && !PBLC->finalinput && PBLC->target != PBLC->tend &&
+				    PRVT->inqlen < PAR_MIN_BYTES) {
+					return (eINFLTResult) (PBLC->status = INFLT_SRCEXHSTD);
+				}
 				continue;
 			case INFLT_TGTEXHSTD:
 				if (PBLC->target == PBLC->tend) {
