@@ -211,6 +211,13 @@ static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned) v) : 32; }
 static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long) v) : 64; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
+/* position of the offset-th set bit of mask at or above base (offset >= 1), 0xffffffff if none */
+static inline unsigned __fns(unsigned mask, unsigned base, int offset)
+{
+	for (unsigned i = base; i < 32; i++)
+		if ((mask >> i) & 1u) { if (--offset == 0) return i; }
+	return 0xffffffffu;
+}
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 static inline unsigned __brev(unsigned v)
 {
