@@ -334,7 +334,7 @@ def _main(real_stdout):
     dom_name, (dom_launches, dom_ms) = dom
     deflate_kernels = {k: v for k, v in prof.items() if not k.startswith("ck_")}
     # one launch of a deflate-pipeline kernel covers one batch: algorithmic bytes = N (read) + C (written)
-    nbatches = max(1, prof.get("lz_kernel", (args.steps,))[0])
+    nbatches = max(1, sum(v[0] for k, v in prof.items() if k.startswith("lz_kernel")) or args.steps)
     alg_bytes_per_launch = (n + produced) * args.steps / nbatches
     achieved = alg_bytes_per_launch / (dom_ms / max(dom_launches, 1) / 1e3) / 1e9 if dom_ms else 0.0
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
@@ -346,7 +346,7 @@ def _main(real_stdout):
     traffic_file = ROOT / "profiles" / "traffic.json"
     if traffic_file.exists():
         try:
-            roofline["traffic"] = json.loads(traffic_file.read_text()).get(dom_name)
+            roofline["traffic"] = json.loads(traffic_file.read_text()).get(dom_name.split("<")[0])
         except Exception:
             pass
 

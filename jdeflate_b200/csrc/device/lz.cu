@@ -393,6 +393,7 @@ lz_parse_phase(LzSmem& S, const LzParams& prm, const uint32_t tid, const uint32_
 	__syncthreads();
 }
 
+template <bool ROUNDS>
 __global__ void __launch_bounds__(LZ_THREADS, 1)
 lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
           const uint16_t* __restrict__ prev, LzParams prm,
@@ -459,6 +460,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 	 * One link, one comparison per position, converged.  It seeds the search
 	 * proper (best so far, chain advanced by one) and, in two-phase mode, feeds a
 	 * tentative parse that tells which positions a parser is likely to visit. */
+	if (ROUNDS)
 	for (uint32_t k = 0; k < PER_THREAD; k++) {
 		const uint32_t p = tid + k * LZ_THREADS;
 		uint32_t result = 0;
@@ -491,8 +493,8 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 	 * match.  The reference searches only where its parser goes, too
 	 * (skipbytes2, src/deflator.c:2729). */
 	for (uint32_t w = tid; w < SEG / 32; w += LZ_THREADS) S.done[w] = 0;
-	for (uint32_t round = 0; round < (prm.twophase ? prm.twophase : 1u); round++) {
-	if (prm.twophase) {
+	for (uint32_t round = 0; round < (ROUNDS ? prm.twophase : 1u); round++) {
+	if (ROUNDS) {
 		lz_parse_phase(S, prm, tid, seg_len);
 		for (uint32_t w = tid; w < SEG / 32; w += LZ_THREADS) {
 			const uint32_t mg = S.merge[w >> 3];
@@ -517,8 +519,6 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 			S.need[w] = nd;
 			S.done[w] |= nd;
 		}
-	} else {
-		for (uint32_t w = tid; w < SEG / 32; w += LZ_THREADS) S.need[w] = 0xffffffffu;
 	}
 	if (tid == 0) S.next_pos = 0;
 	__syncthreads();
@@ -606,6 +606,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 					wnext = g < SEG ? g : SEG;
 					wend = g < SEG ? g + LZ_GRAB : SEG;
 				}
+				if (ROUNDS) {
 				/* the next positions that need a search: set bits of the need bitmap from
 				 * wnext on, within one bitmap word per round */
 				uint32_t nbits = 0;
@@ -655,6 +656,37 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 						cb = S.data[j + best];
 						mode = M_WALK;
 					}
+				}
+				} else {
+				const uint32_t base = wnext;
+				const uint32_t rank = (uint32_t) __popc(fetchers & ((1u << lane) - 1u));
+				const uint32_t have = wend - wnext;
+				const uint32_t want = (uint32_t) __popc(fetchers);
+				wnext += want < have ? want : have;
+				if ((fetchers >> lane) & 1u) {
+					if (p != 0xffffffffu) S.m[p] = best >= MINLEN ? (best << 16) | bestd : 0;
+					p = base + rank;
+					if (rank >= have) {
+						/* block exhausted: next round (or done when the segment is) */
+						if (wend >= SEG) mode = M_DONE;
+						p = 0xffffffffu;
+					}
+					else if (p >= seg_len || seg_len - p < MINLEN) {
+						/* nothing to find here; stay in FETCH */
+						S.m[p] = 0;
+						p = 0xffffffffu;
+					} else {
+						maxlen = seg_len - p;                     /* never past the segment */
+						if (maxlen > MAXLEN) maxlen = MAXLEN;
+						j = hoff + p;
+						jmin = j > WND - 1 ? j - (WND - 1) : 0;
+						if (jmin < first_valid) jmin = first_valid;
+						dmax = j - jmin;
+						best = MINLEN - 1; bestd = 0; cur = j; steps = prm.chain;
+						cb = S.data[j + best];
+						mode = M_WALK;
+					}
+				}
 				}
 			}
 		}
@@ -785,7 +817,8 @@ extern "C" int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
 	static int configured[64];
 	int dev = jdb_rt_get_device();
 	if (dev >= 0 && dev < 64 && !configured[dev]) {
-		cudaFuncSetAttribute(lz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		cudaFuncSetAttribute(lz_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		cudaFuncSetAttribute(lz_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 		configured[dev] = 1;
 	}
 #endif
@@ -799,7 +832,11 @@ extern "C" int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
 	prm.twophase = getenv("JDB_LZ_TWOPHASE") ? (uint32_t) atoi(getenv("JDB_LZ_TWOPHASE")) : (chain >= 128 ? 2u : 0u);
 	prm.short3 = getenv("JDB_LZ_SHORT3") ? (uint32_t) atoi(getenv("JDB_LZ_SHORT3")) : 1u;
 	const uint64_t nseg = (n + SEG - 1) / SEG;
-	JDB_LAUNCH(lz_kernel, dim3((unsigned) nseg), dim3(LZ_THREADS), smem, s,
-	           in, n, chunk_bytes, prev, prm, tok, seg_ntok, seg_hist);
+	if (prm.twophase)
+		JDB_LAUNCH((lz_kernel<true>), dim3((unsigned) nseg), dim3(LZ_THREADS), smem, s,
+		           in, n, chunk_bytes, prev, prm, tok, seg_ntok, seg_hist);
+	else
+		JDB_LAUNCH((lz_kernel<false>), dim3((unsigned) nseg), dim3(LZ_THREADS), smem, s,
+		           in, n, chunk_bytes, prev, prm, tok, seg_ntok, seg_hist);
 	return jdb_rt_check_launch("lz_kernel");
 }
