@@ -416,6 +416,7 @@ struct Stream {
 	uint64_t dst_cap;
 	int final;
 	int count_only;             /* measure a chunk: no output, stop after an empty stored block */
+	int stop_marker;            /* decode ONE chunk: stop after an empty stored block */
 	jdb_inflate_state* st;      /* NULL in batch mode */
 	/* running */
 	uint64_t out;               /* bytes written in this call */
@@ -656,7 +657,7 @@ inflate_stream(WarpMem* m, Stream& s)
 				break;
 			}
 			phase = JDB_INF_HEADER;
-			if (s.count_only && empty_block) {
+			if ((s.count_only || s.stop_marker) && empty_block) {
 				/* the sync / end marker that closes a chunk of our own encoder
 				 * (and of any deflate sync flush) */
 				s.status = ST_MARKER;
@@ -922,7 +923,8 @@ inflate_batch_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__
 		s.dst = dst_base + it.dst_off;
 		s.dst_cap = it.dst_cap;
 		s.final = (int) final;
-		s.count_only = (int) count_only;
+		s.count_only = (int) (count_only & 1u);
+		s.stop_marker = (int) ((count_only >> 1) & 1u);
 		s.st = states ? states + idx : NULL;
 
 		uint32_t zerr = 0;
@@ -1190,6 +1192,7 @@ inflate_fast_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ 
 			s.out = __shfl_sync(JDB_FULL_MASK, (unsigned long long) out, g);
 			s.st = NULL;
 			s.count_only = 0;
+			s.stop_marker = 0;
 			s.ring = NULL;
 			s.ring_lo = 0;
 			s.hist_avail = 0;
@@ -1372,5 +1375,33 @@ extern "C" int jdb_inflate_measure(const uint8_t* src_base, const jdb_inflate_it
 	JDB_LAUNCH(inflate_batch_kernel, dim3(ctas), dim3(INF_THREADS), smem, s,
 	           src_base, (uint8_t*) 0, items, results, (jdb_inflate_state*) 0, count, (uint32_t) JDB_FMT_RAW, 0u,
 	           counter, 0u, 1u);
+	return jdb_rt_check_launch("inflate_batch_kernel");
+}
+
+/* decode mode of the chunk-parallel path: like jdb_inflate_batch (one warp per item, output written),
+ * but every item stops after the first empty stored block it reads -- status JDB_INF_ST_MARKER,
+ * `error` = 1 when that block carried BFINAL */
+extern "C" int jdb_inflate_chunks(const uint8_t* src_base, uint8_t* dst_base,
+                                  const jdb_inflate_item* items, jdb_inflate_result* results,
+                                  uint32_t count, uint32_t* counter, jdb_stream s)
+{
+	if (count == 0) return JDB_OK;
+	int r = jdb_memset_async(counter, 0, sizeof(uint32_t), s);
+	if (r != JDB_OK) return r;
+	const size_t smem = sizeof(WarpMem) * INF_WARPS;
+#ifndef JDB_SIMT_EMU
+	static int configured[64];
+	int dev = jdb_rt_get_device();
+	if (dev >= 0 && dev < 64 && !configured[dev]) {
+		cudaFuncSetAttribute(inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		configured[dev] = 1;
+	}
+#endif
+	uint32_t ctas = (count + INF_WARPS - 1) / INF_WARPS;
+	const uint32_t cap = (uint32_t) jdb_rt_sm_count();
+	if (ctas > cap) ctas = cap;
+	JDB_LAUNCH(inflate_batch_kernel, dim3(ctas), dim3(INF_THREADS), smem, s,
+	           src_base, dst_base, items, results, (jdb_inflate_state*) 0, count, (uint32_t) JDB_FMT_RAW, 0u,
+	           counter, 0u, 2u);
 	return jdb_rt_check_launch("inflate_batch_kernel");
 }

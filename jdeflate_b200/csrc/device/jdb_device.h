@@ -159,6 +159,10 @@ int jdb_marker_scan(const uint8_t* src, uint64_t n, uint32_t* ends, uint32_t max
 int jdb_inflate_measure(const uint8_t* src_base, const jdb_inflate_item* items,
                         jdb_inflate_result* results, uint32_t count,
                         uint32_t* counter, jdb_stream s);
+/* the same with output: every item is decoded into its own dst range and stops after the marker */
+int jdb_inflate_chunks(const uint8_t* src_base, uint8_t* dst_base,
+                       const jdb_inflate_item* items, jdb_inflate_result* results,
+                       uint32_t count, uint32_t* counter, jdb_stream s);
 
 /* ---- deflate pipeline stages (lz.cu, huffman.cu, pack.cu) ---------------- */
 #define JDB_SEG 16384u      /* LZ segment: positions per CTA, histogram granule */

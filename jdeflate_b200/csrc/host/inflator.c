@@ -28,6 +28,9 @@
 /* chunk-parallel decode of one stream (streams cut by sync markers, i.e. ours) */
 #define PAR_MAXC      65536u                  /* marker candidates per step    */
 #define PAR_MIN_BYTES ((size_t) 4 << 20)      /* queued input that makes a step worthwhile */
+#define PAR_MAXFRAG   4096u                   /* chunks decoded per step (slots of par_stride bytes each) */
+#define PAR_STRIDE    ((size_t) 1 << 20)      /* first guess of the slot size: the encoder's largest default chunk */
+#define PAR_STRIDE_MAX ((size_t) 16 << 20)
 #define PAR_AGAIN     0xffu                   /* internal status: a parallel step ran, not at the end */
 
 struct TINFLTPblc {
@@ -62,6 +65,8 @@ struct TINFLTPrvt {
 	uint32 par_ok;
 	uint64 par_total;       /* bytes produced so far (= device total_out) */
 	jdb_dbuf   par_dev;     /* device: candidate ends, items, results */
+	jdb_dbuf   par_scratch; /* device: one slot per candidate chunk */
+	size_t     par_stride;
 	uint8*     par_host;    /* pinned mirror of the same */
 	jdb_dbuf   outbuf;
 
@@ -156,6 +161,9 @@ inflator_reset(TInflator* state)
 	PRVT->inqlen = 0;
 	PRVT->par_ok = 1;
 	PRVT->par_total = 0;
+	if (PRVT->par_stride == 0) {
+		PRVT->par_stride = PAR_STRIDE;
+	}
 
 	{
 		uint32_t* init = (uint32_t*) (PRVT->pinned + 208);
@@ -184,6 +192,7 @@ inflator_destroy(TInflator* state)
 	jdb_dbuf_release(&PRVT->inq);
 	jdb_dbuf_release(&PRVT->outbuf);
 	jdb_dbuf_release(&PRVT->par_dev);
+	jdb_dbuf_release(&PRVT->par_scratch);
 	jdb_pinned_free(PRVT->par_host);
 	jdb_dbuf_release(&PRVT->ckwork);
 	jdb_dev_free(PRVT->dchecks);
@@ -345,17 +354,16 @@ find_u32(const uint32_t* a, uint32_t n, uint32_t v)
  * One chunk-parallel step over the queued input:
  *   1. list every "00 00 FF FF" in the queue (marker_scan_kernel): candidate
  *      chunk ends;
- *   2. decode from the queue start and from every candidate in count mode
- *      (no output) until an empty stored block is read: a real chunk reports
- *      where it ends and how many bytes it decodes to; false candidates just
- *      fail or lead nowhere;
+ *   2. decode from the queue start and from every candidate, one warp each, into
+ *      its own slot of a scratch buffer, stopping at the first empty stored
+ *      block: a real chunk reports where it ends and how many bytes it decoded
+ *      to; false candidates just fail or lead nowhere;
  *   3. follow the chain start -> marker -> marker ... as far as the target has
- *      room; a running sum of the sizes places every chunk;
- *   4. decode the chunks of the chain for real, one warp each, and check that
- *      every one used and produced exactly what step 2 said.
+ *      room, copying every link from its slot to its place in the output.
  * Nothing is assumed about who wrote the stream: a stream without such markers
  * yields an empty chain and the sequential decoder takes over.
- * Returns 1 when it decoded something, 0 when it does not apply, -1 on failure.
+ * Returns 1 when it decoded something, 0 when it does not apply, 2 to be called
+ * again (slot size raised), -1 on failure.
  */
 static int
 parallel_step(struct TINFLTPrvt* state, uint8* dst, size_t cap, size_t* produced_out, int* finished)
@@ -419,31 +427,40 @@ parallel_step(struct TINFLTPrvt* state, uint8* dst, size_t cap, size_t* produced
 	}
 	qsort(h_ends, nc, 4, cmp_u32);
 
-	/* 2. measure from the start and from every candidate that has input after it
-	 * (offsets from here on are relative to the first queued byte) */
+	/* 2. decode from the start and from every candidate that has input after it, each
+	 * into its own slot of a scratch buffer, stopping at the first marker it reads: one
+	 * pass gives both the sizes and the bytes (a slot too small for its chunk just ends
+	 * the chain there).  Offsets from here on are relative to the first queued byte. */
 	ns = 0;
 	h_starts[ns++] = 0;
-	for (i = 0; i < nc; i++) {
+	for (i = 0; i < nc && ns < PAR_MAXFRAG; i++) {
 		if (h_ends[i] > pad && h_ends[i] - pad < n) {
 			h_starts[ns++] = (uint32_t) (h_ends[i] - pad);
 		}
 	}
+	if (jdb_dbuf_reserve(&PRVT->par_scratch, (size_t) ns * PRVT->par_stride) != 0) {
+		return 0;                           /* no memory for the slots: sequential decoder */
+	}
 	for (i = 0; i < ns; i++) {
 		h_items[i].src_off = PRVT->inqoff + h_starts[i];
-		h_items[i].dst_off = 0;
+		h_items[i].dst_off = (uint64_t) i * PRVT->par_stride;
 		h_items[i].src_len = n - h_starts[i];
-		h_items[i].dst_cap = (uint64_t) 1 << 62;
+		h_items[i].dst_cap = PRVT->par_stride;
 	}
 	if (jdb_copy_async(d_items, h_items, (size_t) ns * sizeof(*h_items), PRVT->stream) != JDB_OK ||
-	    jdb_inflate_measure(PRVT->inq.ptr, d_items, d_res, ns, D_COUNTER(PRVT), PRVT->stream) != JDB_OK ||
+	    jdb_inflate_chunks(PRVT->inq.ptr, PRVT->par_scratch.ptr, d_items, d_res, ns, D_COUNTER(PRVT), PRVT->stream) != JDB_OK ||
 	    jdb_copy_async(h_res, d_res, (size_t) ns * sizeof(*h_res), PRVT->stream) != JDB_OK ||
 	    jdb_stream_sync(PRVT->stream) != JDB_OK) {
 		return -1;
 	}
+	if (h_res[0].status == INFLT_TGTEXHSTD && PRVT->par_stride < PAR_STRIDE_MAX) {
+		/* the first chunk does not fit a slot: larger slots next time */
+		PRVT->par_stride *= 4;
+		return 2;
+	}
 
-	/* 3. the chain of real chunks, as far as the target has room; the items of
-	 * the real decode are written over the measured ones as we go (slot nfrag
-	 * is never ahead of the slot k being read) */
+	/* 3. the chain of real chunks, as far as the target has room; every link is copied
+	 * from its slot to its place in the output */
 	total = 0;
 	used = 0;
 	nfrag = 0;
@@ -458,10 +475,10 @@ parallel_step(struct TINFLTPrvt* state, uint8* dst, size_t cap, size_t* produced
 		if (total + r.produced > cap) {
 			break;
 		}
-		h_items[nfrag].src_off = PRVT->inqoff + start;
-		h_items[nfrag].dst_off = total;
-		h_items[nfrag].src_len = r.consumed;
-		h_items[nfrag].dst_cap = r.produced;
+		if (r.produced &&
+		    jdb_copy_async(dst + total, PRVT->par_scratch.ptr + (size_t) k * PRVT->par_stride, (size_t) r.produced, PRVT->stream) != JDB_OK) {
+			return -1;
+		}
 		nfrag++;
 		total += r.produced;
 		used = start + r.consumed;
@@ -473,29 +490,14 @@ parallel_step(struct TINFLTPrvt* state, uint8* dst, size_t cap, size_t* produced
 		if (next >= n) {
 			break;
 		}
-		k = find_u32(h_starts + nfrag, ns - nfrag, (uint32_t) next);
-		if (k == ns - nfrag) {
+		i = find_u32(h_starts + k + 1, ns - (k + 1), (uint32_t) next);
+		if (i == ns - (k + 1)) {
 			break;
 		}
-		k += nfrag;
+		k = k + 1 + i;
 	}
 	if (nfrag == 0) {
 		return 0;
-	}
-
-	/* 4. the real decode */
-	if (jdb_copy_async(d_items, h_items, (size_t) nfrag * sizeof(*h_items), PRVT->stream) != JDB_OK ||
-	    jdb_inflate_batch(PRVT->inq.ptr, dst, d_items, d_res, NULL, nfrag, JDB_FMT_RAW, 0,
-	                      D_COUNTER(PRVT), PRVT->stream) != JDB_OK ||
-	    jdb_copy_async(h_res, d_res, (size_t) nfrag * sizeof(*h_res), PRVT->stream) != JDB_OK ||
-	    jdb_stream_sync(PRVT->stream) != JDB_OK) {
-		return -1;
-	}
-	for (i = 0; i < nfrag; i++) {
-		if (h_res[i].status > INFLT_SRCEXHSTD || h_res[i].produced != h_items[i].dst_cap ||
-		    h_res[i].consumed != h_items[i].src_len) {
-			return -1;
-		}
 	}
 
 	/* the sequential decoder may have to go on from here: leave its state at the
@@ -610,6 +612,9 @@ inflator_inflate(TInflator* state, uint32 final)
 			if (pr < 0) {
 				poison(PRVT, INFLT_EBADSTATE);
 				return INFLT_ERROR;
+			}
+			if (pr == 2) {
+				continue;               /* the slots were too small for the chunks: again with larger ones */
 			}
 			if (pr > 0) {
 				/* not finished: go round again -- more chunks, or the sequential decoder
