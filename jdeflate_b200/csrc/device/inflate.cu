@@ -33,7 +33,6 @@
  * "deviations") are rejected with INFLT_EBADCODE like zlib does.
  */
 #include "common.cuh"
-#include <stdlib.h>
 
 #define INF_WARPS        16
 #define INF_THREADS      (INF_WARPS * 32)
@@ -913,7 +912,7 @@ inflate_batch_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__
 		if (lane == 0) idx = atomicAdd(counter, 1u);
 		idx = __shfl_sync(JDB_FULL_MASK, idx, 0);
 		if (idx >= count) break;
-		/* second pass after inflate_fast_kernel: only what it handed over */
+		/* (a second pass over what an earlier kernel handed over; unused today) */
 		if (redo_only && results[idx].status != ST_REDO) continue;
 
 		const jdb_inflate_item it = items[idx];
@@ -970,279 +969,6 @@ inflate_batch_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__
 	}
 }
 
-/* ---------------------------------------------------------------------------
- * inflate_fast_kernel -- batch decode, FAST_G streams side by side per warp
- * ------------------------------------------------------------------------- */
-
-/*
- * The general decoder above spends 90 % of its instructions in lane 0 (ncu:
- * 4 of 32 lanes active per instruction): Huffman decoding is bit-serial per
- * stream.  For a BATCH the parallel axis is the streams, so here lane g of a
- * warp decodes stream g: the same instruction stream serves FAST_G streams.
- * Rounds of three phases:
- *   headers   streams at a block boundary, one at a time, warp-cooperative
- *             (parse_block_header / build_table, stored blocks copied here)
- *   decode    lanes 0..FAST_G-1, each up to FAST_Q symbols into its queue
- *   emit      queue after queue, all 32 lanes (emit_queue)
- * Only the straight case is handled: a complete, valid stream whose output
- * fits.  Anything else (error, input ends early, target too small, dictionary)
- * is marked ST_REDO and decoded again from its start by inflate_batch_kernel,
- * which owns the exact status / error semantics.
- */
-#define FAST_G   8
-#define FAST_Q   32
-
-struct FastStreamMem {
-	uint32_t lit[LIT_TABLE];
-	uint32_t dist[DIST_TABLE];
-	uint32_t queue[FAST_Q];
-};
-
-struct FastWarpMem {
-	FastStreamMem st[FAST_G];
-	BuildMem bm;
-};
-
-/* refill to more than 32 bits: aligned 32-bit loads, bytes at the edges */
-static __device__ __forceinline__ void
-fast_refill(Bits& b)
-{
-	if (b.bc <= 32) {
-		while (((((uintptr_t) b.p) & 3u) || b.end - b.p < 4) && b.p < b.end && b.bc <= 56) {
-			b.bb |= (uint64_t) (*b.p++) << b.bc;
-			b.bc += 8;
-		}
-		if (b.bc <= 32 && b.end - b.p >= 4) {
-			b.bb |= (uint64_t) (*(const uint32_t*) b.p) << b.bc;
-			b.p += 4;
-			b.bc += 32;
-		}
-	}
-}
-
-__global__ void __launch_bounds__(32)
-inflate_fast_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ dst_base,
-                    const jdb_inflate_item* __restrict__ items, jdb_inflate_result* __restrict__ results,
-                    uint32_t count, uint32_t format, uint32_t* __restrict__ counter)
-{
-	JDB_DYN_SMEM(smem_raw);
-	FastWarpMem& M = *(FastWarpMem*) smem_raw;
-	const unsigned lane = jdb_lane();
-	const bool owner = lane < FAST_G;
-
-	/* per-lane stream slot (meaningful for lane < FAST_G) */
-	uint32_t idx = 0xffffffffu;         /* no stream */
-	bool exhausted = false;             /* the work counter ran out */
-	Bits b; b.bb = 0; b.bc = 0; b.p = 0; b.end = 0;
-	const uint8_t* src0 = 0;            /* first byte of the stream (container header included) */
-	uint64_t src_len = 0;
-	uint8_t* dst = 0;
-	uint64_t dst_cap = 0, out = 0;
-	uint32_t lastblock = 0;
-	bool need_header = false;
-
-	for (;;) {
-		/* ---- (0) take new streams ---- */
-		if (owner && idx == 0xffffffffu && !exhausted) {
-			idx = atomicAdd(counter, 1u);
-			if (idx >= count) { idx = 0xffffffffu; exhausted = true; }
-			else {
-				const jdb_inflate_item it = items[idx];
-				src0 = src_base + it.src_off;
-				src_len = it.src_len;
-				dst = dst_base + it.dst_off;
-				dst_cap = it.dst_cap;
-				out = 0;
-				lastblock = 0;
-				need_header = true;
-				uint32_t head = 0;
-				bool ok = true;
-				if (format == JDB_FMT_ZLIB) {
-					if (src_len < 6) ok = false;            /* header + trailer */
-					else {
-						const uint32_t cmf = src0[0], flg = src0[1];
-						if ((cmf & 15u) != 8 || (cmf >> 4) > 7 || (flg & 0x20u)) ok = false;
-						head = 2;
-					}
-				}
-				b.bb = 0; b.bc = 0;
-				b.p = src0 + head;
-				b.end = src0 + src_len;
-				if (!ok) {
-					jdb_inflate_result r;
-					r.status = ST_REDO; r.error = 0; r.zerror = 0; r.checksum = 0; r.consumed = 0; r.produced = 0;
-					results[idx] = r;
-					idx = 0xffffffffu;
-				}
-			}
-		}
-		if (__ballot_sync(JDB_FULL_MASK, owner && idx != 0xffffffffu) == 0) break;
-
-		uint32_t fail = 0;              /* this lane's stream goes to the general decoder */
-		uint32_t finished = 0;
-
-		/* ---- (1) block headers, one stream at a time ---- */
-		unsigned hm = __ballot_sync(JDB_FULL_MASK, owner && idx != 0xffffffffu && need_header);
-		while (hm) {
-			const int g = __ffs((int) hm) - 1;
-			hm &= hm - 1;
-			Bits hb;
-			hb.bb = __shfl_sync(JDB_FULL_MASK, b.bb, g);
-			hb.bc = __shfl_sync(JDB_FULL_MASK, b.bc, g);
-			hb.p = (const uint8_t*) __shfl_sync(JDB_FULL_MASK, (unsigned long long) b.p, g);
-			hb.end = (const uint8_t*) __shfl_sync(JDB_FULL_MASK, (unsigned long long) b.end, g);
-			const uint32_t lastg = __shfl_sync(JDB_FULL_MASK, lastblock, g);
-			uint32_t r = 0, type = 0, lb = 0;
-			uint32_t done_here = 0;
-			if (lastg) done_here = 1;                                /* the last block has ended */
-			else r = parse_block_header(&M.bm, M.st[g].lit, M.st[g].dist, hb, type, lb);
-			uint64_t copied = 0;
-			if (!done_here && r == 0 && type == 0) {
-				/* stored block: whole bytes of the bit buffer go back, then a plain copy */
-				const uint32_t n = M.bm.scratch[0];
-				uint64_t hp = 0, he = 0;
-				if (lane == 0) {
-					hb.p -= hb.bc >> 3;
-					hb.bb = 0;
-					hb.bc = 0;
-					hp = (uint64_t) hb.p;
-					he = (uint64_t) hb.end;
-				}
-				hp = __shfl_sync(JDB_FULL_MASK, (unsigned long long) hp, 0);
-				he = __shfl_sync(JDB_FULL_MASK, (unsigned long long) he, 0);
-				const uint64_t og = __shfl_sync(JDB_FULL_MASK, (unsigned long long) out, g);
-				const uint64_t cg = __shfl_sync(JDB_FULL_MASK, (unsigned long long) dst_cap, g);
-				uint8_t* dg = (uint8_t*) __shfl_sync(JDB_FULL_MASK, (unsigned long long) dst, g);
-				if ((uint64_t) n > he - hp || (uint64_t) n > cg - og) r = 1;      /* does not fit: general decoder */
-				else {
-					const uint8_t* sp = (const uint8_t*) hp;
-					for (uint32_t j = lane; j < n; j += 32) dg[og + j] = sp[j];
-					copied = n;
-					if (lane == 0) hb.p += n;
-				}
-				__syncwarp();
-			}
-			/* state back to the owning lane */
-			const uint64_t nbb = __shfl_sync(JDB_FULL_MASK, (unsigned long long) hb.bb, 0);
-			const uint32_t nbc = __shfl_sync(JDB_FULL_MASK, hb.bc, 0);
-			const uint64_t np = __shfl_sync(JDB_FULL_MASK, (unsigned long long) hb.p, 0);
-			if ((int) lane == g) {
-				if (done_here) finished = 1;
-				else if (r != 0) fail = 1;
-				else {
-					b.bb = nbb; b.bc = nbc; b.p = (const uint8_t*) np;
-					lastblock = lb;
-					out += copied;
-					need_header = (type == 0);          /* after a stored block comes the next header */
-				}
-			}
-			/* a stored block may be followed by more headers of the same stream: next round */
-		}
-
-		/* ---- (2) decode: every owning lane its own stream ---- */
-		uint32_t nq = 0;
-		if (owner && idx != 0xffffffffu && !need_header && !fail && !finished) {
-			const uint32_t* lit = M.st[lane].lit;
-			const uint32_t* dtab = M.st[lane].dist;
-			uint32_t* queue = M.st[lane].queue;
-			const uint64_t room = dst_cap - out;
-			uint64_t qbytes = 0;
-			while (nq < FAST_Q) {
-				fast_refill(b);
-				uint32_t e = lookup(lit, b.bb, LIT_ROOT);
-				uint32_t nb = e & 15u;
-				if (nb == 0 || nb > b.bc) { fail = 1; break; }
-				const uint32_t type = (e >> 8) & 3u;
-				if (type == T_LIT) {
-					if (qbytes >= room) { fail = 1; break; }
-					bits_take(b, nb);
-					queue[nq++] = e >> 16;
-					qbytes++;
-					continue;
-				}
-				bits_take(b, nb);
-				if (type == T_EOB) { need_header = true; break; }
-				if ((e >> 16) == 0) { fail = 1; break; }
-				uint32_t xb = (e >> 4) & 15u;
-				if (xb > b.bc) { fail = 1; break; }
-				const uint32_t len = (e >> 16) + bits_take(b, xb);
-				fast_refill(b);
-				const uint32_t d = lookup(dtab, b.bb, DIST_ROOT);
-				nb = d & 15u;
-				if (nb == 0 || nb > b.bc || (d >> 16) == 0) { fail = 1; break; }
-				bits_take(b, nb);
-				xb = (d >> 4) & 15u;
-				if (xb > b.bc) { fail = 1; break; }
-				const uint32_t dd = (d >> 16) + bits_take(b, xb);
-				if ((uint64_t) dd > out + qbytes || qbytes + len > room) { fail = 1; break; }
-				queue[nq++] = (len << 16) | dd;
-				qbytes += len;
-			}
-		}
-		__syncwarp();
-
-		/* ---- (3) emit: queue after queue, all lanes ---- */
-#pragma unroll 1
-		for (int g = 0; g < FAST_G; g++) {
-			const uint32_t nqg = __shfl_sync(JDB_FULL_MASK, fail ? 0u : nq, g);
-			if (nqg == 0) continue;
-			Stream s;
-			s.dst = (uint8_t*) __shfl_sync(JDB_FULL_MASK, (unsigned long long) dst, g);
-			s.dst_cap = __shfl_sync(JDB_FULL_MASK, (unsigned long long) dst_cap, g);
-			s.out = __shfl_sync(JDB_FULL_MASK, (unsigned long long) out, g);
-			s.st = NULL;
-			s.count_only = 0;
-			s.stop_marker = 0;
-			s.ring = NULL;
-			s.ring_lo = 0;
-			s.hist_avail = 0;
-			s.total_before = 0;
-			uint32_t pl = 0, pd = 0;
-			emit_queue(s, &M.bm, M.st[g].queue, nqg, pl, pd);
-			if ((int) lane == g) out = s.out;
-			__syncwarp();
-		}
-
-		/* ---- (4) streams that ended: trailer, result ---- */
-		unsigned fm = __ballot_sync(JDB_FULL_MASK, owner && idx != 0xffffffffu && (finished || fail));
-		while (fm) {
-			const int g = __ffs((int) fm) - 1;
-			fm &= fm - 1;
-			const uint32_t failg = __shfl_sync(JDB_FULL_MASK, fail, g);
-			uint32_t adler = 0;
-			if (!failg && format == JDB_FMT_ZLIB) {
-				const uint8_t* dg = (const uint8_t*) __shfl_sync(JDB_FULL_MASK, (unsigned long long) dst, g);
-				const uint64_t og = __shfl_sync(JDB_FULL_MASK, (unsigned long long) out, g);
-				adler = warp_adler32(dg, og);
-			}
-			if ((int) lane == g) {
-				jdb_inflate_result r;
-				r.status = ST_REDO; r.error = 0; r.zerror = 0; r.checksum = 0; r.consumed = 0; r.produced = 0;
-				if (!fail) {
-					/* whole unread bytes go back to the input */
-					b.p -= b.bc >> 3;
-					uint64_t used = (uint64_t) (b.p - src0);
-					r.status = ST_OK;
-					r.produced = out;
-					if (format == JDB_FMT_ZLIB) {
-						r.checksum = adler;
-						if (used + 4 > src_len) r.status = ST_REDO;      /* trailer missing: general decoder reports it */
-						else {
-							const uint8_t* t = src0 + used;
-							const uint32_t want = ((uint32_t) t[0] << 24) | ((uint32_t) t[1] << 16) | ((uint32_t) t[2] << 8) | t[3];
-							if (want != adler) r.zerror = JDB_ZERR_CHECKSUM;
-							used += 4;
-						}
-					}
-					r.consumed = used;
-				}
-				results[idx] = r;
-				idx = 0xffffffffu;
-			}
-		}
-	}
-}
-
 extern "C" size_t jdb_inflate_state_bytes(void) { return sizeof(jdb_inflate_state); }
 
 extern "C" int jdb_inflate_batch(const uint8_t* src_base, uint8_t* dst_base,
@@ -1262,34 +988,7 @@ extern "C" int jdb_inflate_batch(const uint8_t* src_base, uint8_t* dst_base,
 		configured[dev] = 1;
 	}
 #endif
-	uint32_t redo_only = 0;
-	/* Measured on B200 (4-64 KiB zlib JSON records): 11.9 GB/s against 24 GB/s for the general
-	 * decoder -- with 58 KB of tables per warp only three warps fit an SM and the eight emit
-	 * phases of a round serialise their L2 round trips.  Kept opt-in (JDB200_FAST_INFLATE=1)
-	 * until the emit phase is batched across the eight queues. */
-	if (states == NULL && final && count >= FAST_G && getenv("JDB200_FAST_INFLATE") && !getenv("JDB200_NO_FAST_INFLATE")) {
-		/* batch of complete streams: FAST_G streams per warp first, the general
-		 * decoder afterwards for whatever the fast path handed over */
-		const size_t fsmem = sizeof(FastWarpMem);
-#ifndef JDB_SIMT_EMU
-		static int fconfigured[64];
-		if (dev >= 0 && dev < 64 && !fconfigured[dev]) {
-			cudaFuncSetAttribute(inflate_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fsmem);
-			fconfigured[dev] = 1;
-		}
-#endif
-		uint32_t fctas = (count + FAST_G - 1) / FAST_G;
-		const uint32_t fcap = (uint32_t) jdb_rt_sm_count() * 3;
-		if (fctas > fcap) fctas = fcap;
-		JDB_LAUNCH(inflate_fast_kernel, dim3(fctas), dim3(32), fsmem, s,
-		           src_base, dst_base, items, results, count, format, counter);
-		r = jdb_rt_check_launch("inflate_fast_kernel");
-		if (r != JDB_OK) return r;
-		r = jdb_memset_async(counter, 0, sizeof(uint32_t), s);
-		if (r != JDB_OK) return r;
-		redo_only = 1;
-		if (getenv("JDB200_FAST_INFLATE_ONLY")) return JDB_OK;      /* diagnostics: leave ST_REDO marks visible */
-	}
+	const uint32_t redo_only = 0;
 	uint32_t ctas = (count + INF_WARPS - 1) / INF_WARPS;
 	uint32_t cap = (uint32_t) jdb_rt_sm_count();
 	if (ctas > cap) ctas = cap;
@@ -1308,7 +1007,7 @@ extern "C" int jdb_inflate_batch(const uint8_t* src_base, uint8_t* dst_base,
  * aligned empty stored block .. 00 00 FF FF.  marker_scan_kernel lists the end
  * offsets of every occurrence of those four bytes -- candidates only: the same
  * bytes can occur inside compressed data.  The caller decodes from every
- * candidate in count mode (jdb_inflate_measure) and keeps the chain that starts
+ * candidate (jdb_inflate_chunks) and keeps the chain that starts
  * at the true stream position and hops from marker to marker.
  */
 __global__ void __launch_bounds__(256)
@@ -1346,36 +1045,6 @@ extern "C" int jdb_marker_scan(const uint8_t* src, uint64_t n, uint32_t* ends, u
 	if (ctas > cap) ctas = cap;
 	JDB_LAUNCH(marker_scan_kernel, dim3(ctas), dim3(256), 0, s, src, n, ends, max_ends, count);
 	return jdb_rt_check_launch("marker_scan_kernel");
-}
-
-/* count mode: per item, decode from src_off without producing output until an
- * empty stored block has been read.  results[i]: status ST_MARKER (4) with
- * `consumed` = bytes up to and including the marker, `produced` = bytes the
- * chunk decodes to, `error` = 1 when the marker carried BFINAL; anything else
- * means "not a chunk of this shape". */
-extern "C" int jdb_inflate_measure(const uint8_t* src_base, const jdb_inflate_item* items,
-                                   jdb_inflate_result* results, uint32_t count,
-                                   uint32_t* counter, jdb_stream s)
-{
-	if (count == 0) return JDB_OK;
-	int r = jdb_memset_async(counter, 0, sizeof(uint32_t), s);
-	if (r != JDB_OK) return r;
-	const size_t smem = sizeof(WarpMem) * INF_WARPS;
-#ifndef JDB_SIMT_EMU
-	static int configured[64];
-	int dev = jdb_rt_get_device();
-	if (dev >= 0 && dev < 64 && !configured[dev]) {
-		cudaFuncSetAttribute(inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		configured[dev] = 1;
-	}
-#endif
-	uint32_t ctas = (count + INF_WARPS - 1) / INF_WARPS;
-	const uint32_t cap = (uint32_t) jdb_rt_sm_count();
-	if (ctas > cap) ctas = cap;
-	JDB_LAUNCH(inflate_batch_kernel, dim3(ctas), dim3(INF_THREADS), smem, s,
-	           src_base, (uint8_t*) 0, items, results, (jdb_inflate_state*) 0, count, (uint32_t) JDB_FMT_RAW, 0u,
-	           counter, 0u, 1u);
-	return jdb_rt_check_launch("inflate_batch_kernel");
 }
 
 /* decode mode of the chunk-parallel path: like jdb_inflate_batch (one warp per item, output written),

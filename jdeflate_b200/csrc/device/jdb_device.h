@@ -155,11 +155,10 @@ int jdb_inflate_batch(const uint8_t* src_base, uint8_t* dst_base,
 /* chunk discovery for the parallel decode of one large stream (inflate.cu) */
 int jdb_marker_scan(const uint8_t* src, uint64_t n, uint32_t* ends, uint32_t max_ends,
                     uint32_t* count, jdb_stream s);
-#define JDB_INF_ST_MARKER 4u       /* jdb_inflate_measure: stopped after an empty stored block */
-int jdb_inflate_measure(const uint8_t* src_base, const jdb_inflate_item* items,
-                        jdb_inflate_result* results, uint32_t count,
-                        uint32_t* counter, jdb_stream s);
-/* the same with output: every item is decoded into its own dst range and stops after the marker */
+#define JDB_INF_ST_MARKER 4u       /* jdb_inflate_chunks: stopped after an empty stored block */
+/* every item is decoded into its own dst range and stops after the first empty stored block it
+ * reads: status JDB_INF_ST_MARKER, `consumed` up to and including the marker, `produced` bytes
+ * written, `error` = 1 when the marker carried BFINAL */
 int jdb_inflate_chunks(const uint8_t* src_base, uint8_t* dst_base,
                        const jdb_inflate_item* items, jdb_inflate_result* results,
                        uint32_t count, uint32_t* counter, jdb_stream s);

@@ -144,28 +144,6 @@ def test_batch_api(lib, oracle, corpus):
     assert res[0].status == api.OK and res[0].zerror == api.ZSTRM_ECHECKSUM
 
 
-def test_lane_parallel_batch_path_matches_general_decoder(lib, corpus, monkeypatch):
-    """The opt-in lane-per-stream batch kernel (JDB200_FAST_INFLATE=1) hands anything unusual to
-    the general decoder; per-record results must be identical with and without it."""
-    recs = [corpus.json_record(i) for i in range(24)] + [corpus.fill(3, 20000), b"", b"q"]
-    streams = [zlib.compress(r, (1, 6, 9)[i % 3]) for i, r in enumerate(recs)]
-    bad = bytearray(streams[2]); bad[len(bad) // 2] ^= 0x11
-    streams[2] = bytes(bad)
-    streams[4] = streams[4][:-7]
-    caps = [len(r) for r in recs]
-    caps[6] //= 2
-
-    def run():
-        outs, res = lib.inflate_batch_bytes(streams, caps, fmt=api.JDB200_ZLIB)
-        return [(o if q.status == 0 and q.zerror == 0 else None, q.status, q.error, q.zerror, q.srcused, q.tgtused)
-                for o, q in zip(outs, res)]
-    general = run()
-    monkeypatch.setenv("JDB200_FAST_INFLATE", "1")
-    fast = run()
-    assert fast == general
-    assert general[0][0] == recs[0] and general[-1][0] == recs[-1]
-
-
 def _flushed_stream(data, piece, mode):
     """Raw deflate by zlib with a flush of `mode` after every `piece` bytes."""
     co = zlib.compressobj(6, zlib.DEFLATED, -15)
