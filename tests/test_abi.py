@@ -79,3 +79,24 @@ def test_no_cpu_fallback_without_a_device(product):
     assert not product.lib.inflator_create(0, None)
     assert not product.lib.zstrm_create(api.ZSTRM_DEFLATE | api.ZSTRM_GZIP, 6, None)
     assert product.lib.jdb200_device_count() == 0
+
+
+def _build_example(tmp_path):
+    exe = tmp_path / "roundtrip"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", str(ROOT / "examples" / "roundtrip.c"),
+                    "-I", str(ROOT / "include"), "-L", str(lib_path().parent), "-ljdeflate",
+                    f"-Wl,-rpath,{lib_path().parent}", "-o", str(exe)], check=True)
+    return exe
+
+
+def test_c_program_written_for_the_reference_links(product, tmp_path):
+    """examples/roundtrip.c uses only the reference's C API (the README loops); it must compile
+    against include/ and link against libjdeflate.so unchanged."""
+    assert _build_example(tmp_path).exists()
+
+
+@pytest.mark.gpu
+def test_c_program_runs_on_the_gpu(product, tmp_path):
+    res = subprocess.run([str(_build_example(tmp_path))], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "raw:" in res.stdout and "gzip:" in res.stdout and "round trip ok" in res.stdout
