@@ -350,6 +350,29 @@ def _main(real_stdout):
         except Exception:
             pass
 
+    # ---- checksums of the same 1 GiB (device-resident): HBM-read bound ---------------------------------
+    checksum = {}
+    try:
+        for name, fn, start in (("crc32", jd.lib.zstrm_crc32update, 0xFFFFFFFF), ("adler32", jd.lib.zstrm_adler32update, 1)):
+            fn(start, dev_in.data_ptr(), n)
+            jd.profile(True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps = 10
+            for _ in range(reps):
+                got = fn(start, dev_in.data_ptr(), n)
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) / reps
+            kp = jd.profile_read()
+            jd.profile(False)
+            kms = sum(v[1] for k, v in kp.items() if k.startswith("ck_")) / reps
+            want = zlib.crc32(host_in.numpy()) ^ 0xFFFFFFFF if name == "crc32" else zlib.adler32(host_in.numpy())
+            assert got == want, name
+            checksum[name] = {"value": round(n / wall / 1e9, 1), "unit": "GB/s", "kernel_GBps": round(n / (kms / 1e3) / 1e9, 1),
+                              "frac_of_hbm_peak": round(n / (kms / 1e3) / 1e9 / peak, 4)}
+    except Exception as ex:                                           # reported, never required
+        checksum = {"note": f"failed: {ex}"}
+
     # ---- e2e: zstrm API, host buffers -----------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -447,7 +470,7 @@ def _main(real_stdout):
             "config": workload_config(args, {"chunk_kib": int(os.environ.get("JDB200_CHUNK_KIB", "512")),
                                              "collective": "all_gather of 24 B per rank" if world > 1 else "none"}),
             "ratio": round(n / produced, 4), "compressed_bytes_per_gpu": produced,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "inflate": inflate,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "inflate": inflate, "checksum": checksum,
             "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), file=real_stdout, flush=True)
