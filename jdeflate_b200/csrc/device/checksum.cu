@@ -20,6 +20,13 @@
  *   is a plain xor; Adler-32 partials are position weighted the same way so
  *   their combine is a plain sum modulo 65521.
  *   Algorithmic traffic: N bytes read, 16 bytes written per CTA.
+ *
+ *   Large inputs (>= CKW_MIN_BYTES) take ck_wide_kernel: the same scheme with
+ *   1024 threads and one CTA per SM, whose row table is replicated 32 times in
+ *   shared memory (entry e of lane l lives at word e * 32 + l, i.e. in bank l)
+ *   so that the 16 data dependent lookups per vector never collide.  The
+ *   256-thread kernel loses two thirds of its shared-memory wavefronts to bank
+ *   conflicts (profiles/r1_checksum_kernel_ncu_summary.txt).
  */
 #include "common.cuh"
 #include <stdlib.h>
@@ -35,7 +42,13 @@
 #define ZT_4    0      /* advance by 4 bytes    (classic slice-by-4 tables) */
 #define ZT_ROW  1      /* advance by 4096 bytes */
 #define ZT_W0   2      /* advance by 128 bytes  */
-#define ZT_SETS 3
+#define ZT_WROW 3      /* advance by 16384 bytes (row of the wide kernel) */
+#define ZT_SETS 4
+
+#define CKW_THREADS   1024
+#define CKW_ROW_BYTES (CKW_THREADS * 16)     /* 16384 */
+#define CKW_REP_WORDS (4 * 256 * 32)         /* row table, one copy per bank */
+#define CKW_SMEM      ((CKW_REP_WORDS + CKW_THREADS * 4 + 3 * 1024) * 4)
 
 struct CkTables {
 	uint32_t z[ZT_SETS][4][256];
@@ -85,7 +98,7 @@ static void build_tables(CkTables* t)
 	t->xpow[0] = x8;
 	for (int k = 1; k < 64; k++) t->xpow[k] = gf2_mulmod(t->xpow[k - 1], t->xpow[k - 1]);
 
-	const uint64_t adv[ZT_SETS] = { 4, CK_ROW_BYTES, 128 };
+	const uint64_t adv[ZT_SETS] = { 4, CK_ROW_BYTES, 128, CKW_ROW_BYTES };
 	for (int s = 0; s < ZT_SETS; s++) {
 		uint32_t m = gf2_xpow8(t->xpow, adv[s]);
 		for (int k = 0; k < 4; k++)
@@ -243,6 +256,176 @@ ck_partial_kernel(const uint4* __restrict__ body, uint64_t nvec, uint32_t nctas,
 	if (tid == 0) out[g].crc = crc;
 }
 
+/* lookups into the bank-replicated row table: L already points at the lane's bank */
+/* byte k of r selects the entry: PRMT isolates the byte (ALU pipe), the scaled add
+ * to the lane's bank goes to the FMA pipe as an IMAD -- the shift/mask/or form kept
+ * the ALU pipe busy 3 ops per lookup and capped the kernel at 4.8 TB/s */
+#ifdef JDB_SIMT_EMU
+#define ZIDX(r, k, lb) (((((r) >> (8 * (k))) & 0xffu) << 7) + (lb))
+#else
+static __device__ __forceinline__ uint32_t zidx_(uint32_t r, uint32_t sel, uint32_t lb)
+{
+	uint32_t b, a;
+	asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(r), "r"(sel));
+	asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(a) : "r"(b), "r"(lb));
+	return a;
+}
+#define ZIDX(r, k, lb) zidx_((r), 0x4440u + (k), (lb))
+#endif
+/* lb = byte offset of the lane's bank inside the replicated table */
+#define ZLD(R, off) (*(const uint32_t*) ((const unsigned char*) (R) + (off)))
+#define ZREP(R, lb, r) (ZLD(R, ZIDX(r, 0, lb)) ^ ZLD(R, 32768u + ZIDX(r, 1, lb)) ^ \
+                        ZLD(R, 65536u + ZIDX(r, 2, lb)) ^ ZLD(R, 98304u + ZIDX(r, 3, lb)))
+
+template <bool DO_CRC, bool DO_ADLER>
+__global__ void __launch_bounds__(CKW_THREADS, 1)
+ck_wide_kernel(const uint4* __restrict__ body, uint64_t nvec, uint32_t nctas,
+               const CkTables* __restrict__ tables, CkPartial* __restrict__ out)
+{
+	JDB_DYN_SMEM(dyn);
+	uint32_t* rep = (uint32_t*) dyn;                                   /* [4][256][32] */
+	uint32_t* row = rep + CKW_REP_WORDS;                               /* [4096]       */
+	uint32_t (*zrow)[256] = (uint32_t (*)[256]) (row + CKW_THREADS * 4);
+	uint32_t (*z4)[256]   = zrow + 4;
+	uint32_t (*zw0)[256]  = z4 + 4;
+	__shared__ unsigned long long red[2][CKW_THREADS / 32];
+
+	const uint32_t tid = threadIdx.x;
+	const uint32_t g = blockIdx.x;
+
+	if (DO_CRC) {
+		const uint32_t* src = &tables->z[ZT_WROW][0][0];
+		for (uint32_t i = tid; i < CKW_REP_WORDS; i += CKW_THREADS) rep[i] = src[i >> 5];
+		(&zrow[0][0])[tid] = (&tables->z[ZT_ROW][0][0])[tid];
+		(&z4[0][0])[tid]   = (&tables->z[ZT_4][0][0])[tid];
+		(&zw0[0][0])[tid]  = (&tables->z[ZT_W0][0][0])[tid];
+	}
+	__syncthreads();
+
+	const uint64_t v0 = nvec * g / nctas;
+	const uint64_t v1 = nvec * (g + 1) / nctas;
+	const uint64_t span = v1 - v0;
+	const uint64_t rows = (span + CKW_THREADS - 1) / CKW_THREADS;
+	const uint64_t pad = rows * CKW_THREADS - span;       /* right aligned, see above */
+	const uint32_t lb = (tid & 31u) * 4;
+
+	uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+	unsigned long long sa = 0, sb = 0, sw = 0;
+
+	/* Adler-32: a byte at span offset o weighs (span_bytes - o).  The weight of a
+	 * thread's vector drops by one row (16384) per iteration, so with sa the running
+	 * byte sum, sb += sa before each row leaves sb = sum_j s_j * (rows after j) and
+	 * the weighted sum is w_last * sa + 16384 * sb - (in-vector offsets, sw) */
+#define CKW_ADLER(v) do { \
+		uint32_t s_ = __dp4a((v).x, 0x01010101u, 0u); \
+		s_ = __dp4a((v).y, 0x01010101u, s_); \
+		s_ = __dp4a((v).z, 0x01010101u, s_); \
+		s_ = __dp4a((v).w, 0x01010101u, s_); \
+		uint32_t w_ = __dp4a((v).x, 0x03020100u, 0u); \
+		w_ = __dp4a((v).y, 0x07060504u, w_); \
+		w_ = __dp4a((v).z, 0x0b0a0908u, w_); \
+		w_ = __dp4a((v).w, 0x0f0e0d0cu, w_); \
+		sb += sa; sa += s_; sw += w_; \
+	} while (0)
+
+	if (rows) {
+		/* first row: the only one with empty slots */
+		if (tid >= pad) {
+			const uint4 v = __ldg(body + v0 + (tid - pad));
+			if (DO_CRC) { c0 = v.x; c1 = v.y; c2 = v.z; c3 = v.w; }
+			if (DO_ADLER) CKW_ADLER(v);
+		}
+		const uint4* p = body + v0 + (CKW_THREADS - pad) + tid;
+		uint64_t j = 1;
+		for (; j + 4 <= rows; j += 4) {
+			const uint4 va = __ldg(p);
+			const uint4 vb = __ldg(p + CKW_THREADS);
+			const uint4 vc = __ldg(p + 2 * CKW_THREADS);
+			const uint4 vd = __ldg(p + 3 * CKW_THREADS);
+			p += 4 * CKW_THREADS;
+			if (DO_CRC) {
+				c0 = ZREP(rep, lb, c0) ^ va.x; c1 = ZREP(rep, lb, c1) ^ va.y; c2 = ZREP(rep, lb, c2) ^ va.z; c3 = ZREP(rep, lb, c3) ^ va.w;
+				c0 = ZREP(rep, lb, c0) ^ vb.x; c1 = ZREP(rep, lb, c1) ^ vb.y; c2 = ZREP(rep, lb, c2) ^ vb.z; c3 = ZREP(rep, lb, c3) ^ vb.w;
+				c0 = ZREP(rep, lb, c0) ^ vc.x; c1 = ZREP(rep, lb, c1) ^ vc.y; c2 = ZREP(rep, lb, c2) ^ vc.z; c3 = ZREP(rep, lb, c3) ^ vc.w;
+				c0 = ZREP(rep, lb, c0) ^ vd.x; c1 = ZREP(rep, lb, c1) ^ vd.y; c2 = ZREP(rep, lb, c2) ^ vd.z; c3 = ZREP(rep, lb, c3) ^ vd.w;
+			}
+			if (DO_ADLER) {
+				CKW_ADLER(va);
+				CKW_ADLER(vb);
+				CKW_ADLER(vc);
+				CKW_ADLER(vd);
+			}
+		}
+		for (; j < rows; j++) {
+			const uint4 v = __ldg(p);
+			p += CKW_THREADS;
+			if (DO_CRC) { c0 = ZREP(rep, lb, c0) ^ v.x; c1 = ZREP(rep, lb, c1) ^ v.y; c2 = ZREP(rep, lb, c2) ^ v.z; c3 = ZREP(rep, lb, c3) ^ v.w; }
+			if (DO_ADLER) CKW_ADLER(v);
+		}
+	}
+#undef CKW_ADLER
+
+	uint32_t crc = 0;
+	if (DO_CRC) {
+		row[tid * 4 + 0] = c0;
+		row[tid * 4 + 1] = c1;
+		row[tid * 4 + 2] = c2;
+		row[tid * 4 + 3] = c3;
+		__syncthreads();
+		/* 4096 words -> 1024 columns of a 4 KiB row */
+		uint32_t r = 0;
+		for (int k = 0; k < 4; k++) {
+			r = ZMUL(zrow, r);
+			r ^= row[k * CKW_THREADS + tid];
+		}
+		__syncthreads();
+		row[tid] = r;
+		__syncthreads();
+		if (tid < 32) {
+			/* 1024 words -> 32 columns of a 128 byte row */
+			r = 0;
+			for (int k = 0; k < 32; k++) {
+				r = ZMUL(zw0, r);
+				r ^= row[k * 32 + tid];
+			}
+			__syncwarp();
+			row[tid] = r;
+			__syncwarp();
+			if (tid == 0) {
+				uint32_t f = 0;
+				for (int l = 0; l < 32; l++) {
+					f ^= row[l];
+					f = ZMUL(z4, f);
+				}
+				const uint64_t after = (nvec - v1) * 16;
+				crc = gf2_mulmod(f, gf2_xpow8(tables->xpow, after));
+			}
+		}
+	}
+
+	if (DO_ADLER) {
+		const unsigned long long wlast = (unsigned long long) (CKW_THREADS - tid) * 16;
+		unsigned long long b = (wlast * sa + (sb % ADLER_MOD) * CKW_ROW_BYTES - sw) % ADLER_MOD;
+		unsigned long long a = sa % ADLER_MOD;
+		for (int o = 16; o; o >>= 1) {
+			a += __shfl_down_sync(JDB_FULL_MASK, a, o);
+			b += __shfl_down_sync(JDB_FULL_MASK, b, o);
+		}
+		if ((tid & 31) == 0) { red[0][tid >> 5] = a; red[1][tid >> 5] = b; }
+		__syncthreads();
+		if (tid == 0) {
+			a = 0; b = 0;
+			for (int w = 0; w < CKW_THREADS / 32; w++) { a += red[0][w]; b += red[1][w]; }
+			a %= ADLER_MOD;
+			const uint64_t after = (nvec - v1) * 16;
+			b = (b + (after % ADLER_MOD) * a) % ADLER_MOD;
+			out[g].a = (uint32_t) a;
+			out[g].b = (uint32_t) b;
+		}
+	}
+	if (tid == 0) out[g].crc = crc;
+}
+
 /*
  * Ordered combine: head bytes (before 16-byte alignment), the xor / sum of the
  * CTA partials, tail bytes.  One warp; the serial parts touch < 32 bytes.
@@ -296,6 +479,13 @@ ck_combine_kernel(const uint8_t* data, uint32_t nhead, uint64_t nbody, uint32_t 
 
 /* ---- launcher ---------------------------------------------------------- */
 
+/* smallest body that takes the wide kernel (its 128 KiB table fill has to pay) */
+static uint64_t ckw_min_bytes(void)
+{
+	const char* e = getenv("JDB200_CK_WIDE_MIN_KIB");
+	return e && atoll(e) > 0 ? (uint64_t) atoll(e) << 10 : (uint64_t) 16 << 20;
+}
+
 extern "C" size_t jdb_checksum_workspace_bytes(void)
 {
 	return sizeof(CkPartial) * CK_MAX_CTAS;
@@ -316,7 +506,34 @@ extern "C" int jdb_checksum(const uint8_t* data, size_t n, int which,
 	uint64_t nvec = nbody / 16;
 
 	uint32_t nctas = 0;
-	if (nvec) {
+	if (nvec && nbody >= ckw_min_bytes()) {
+		/* one CTA per SM, at least 128 KiB each */
+		static int attr_done[64];
+		int dev = jdb_rt_get_device();
+		if (dev < 0 || dev >= 64) dev = 0;
+#ifndef JDB_SIMT_EMU
+		if (!attr_done[dev]) {
+			cudaFuncSetAttribute(ck_wide_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CKW_SMEM);
+			cudaFuncSetAttribute(ck_wide_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CKW_SMEM);
+			cudaFuncSetAttribute(ck_wide_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CKW_SMEM);
+			attr_done[dev] = 1;
+		}
+#endif
+		uint64_t want = nbody >> 17;
+		uint64_t cap = (uint64_t) jdb_rt_sm_count();
+		nctas = (uint32_t) (want < cap ? want : cap);
+		if (nctas == 0) nctas = 1;
+		const uint4* body = (const uint4*) (data + nhead);
+		CkPartial* parts = (CkPartial*) work;
+		if ((which & JDB_CK_CRC32) == 0)
+			JDB_LAUNCH((ck_wide_kernel<false, true>), dim3(nctas), dim3(CKW_THREADS), CKW_SMEM, s, body, nvec, nctas, tables, parts);
+		else if (which & JDB_CK_ADLER32)
+			JDB_LAUNCH((ck_wide_kernel<true, true>), dim3(nctas), dim3(CKW_THREADS), CKW_SMEM, s, body, nvec, nctas, tables, parts);
+		else
+			JDB_LAUNCH((ck_wide_kernel<true, false>), dim3(nctas), dim3(CKW_THREADS), CKW_SMEM, s, body, nvec, nctas, tables, parts);
+		int r = jdb_rt_check_launch("ck_wide_kernel");
+		if (r != JDB_OK) return r;
+	} else if (nvec) {
 		/* at least 64 KiB per CTA, at most 4 CTAs per SM */
 		uint64_t want = (nbody + 65535) / 65536;
 		uint64_t cap = (uint64_t) jdb_rt_sm_count() * 4;

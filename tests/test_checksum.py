@@ -58,3 +58,28 @@ def test_crc_combine(lib, oracle, corpus, golden):
     assert acc == zlib.crc32(d)
     # 64-bit lengths (the reference takes a u32 length, src/zstrm.c:1428)
     assert lib.crc32_combine(0x12345678, 0x9abcdef0, (1 << 33) + 5) == oracle.crc32_combine(0x12345678, 0x9abcdef0, (1 << 33) + 5)
+
+
+def test_wide_kernel_sizes(lib, corpus, monkeypatch):
+    """Inputs of 16 MiB and more take ck_wide_kernel (1024 threads, bank-replicated row table);
+    the threshold is lowered here so every span / padding shape of it is exercised at sizes zlib
+    finishes quickly: fewer vectors than threads, ragged first rows, the 4-row unrolled loop and
+    its remainder, unaligned heads and tails."""
+    monkeypatch.setenv("JDB200_CK_WIDE_MIN_KIB", "1")
+    big = corpus.fill(5, 3 << 20, offset=(4 << 20) - (1 << 20))
+    for off, n in ((0, 1024), (1, 1040), (3, 16384 + 17), (0, 16384 * 5), (5, 16384 * 9 + 4001),
+                   (0, 131072), (7, 262144 + 33), (2, 1 << 20), (9, (3 << 20) - 9)):
+        d = big[off:off + n]
+        assert lib.crc32(d) == zlib.crc32(d), (off, n)
+        assert lib.adler32(d) == zlib.adler32(d), (off, n)
+    ff = b"\xff" * ((2 << 20) + 5)
+    assert lib.adler32(ff) == zlib.adler32(ff) and lib.crc32(ff) == zlib.crc32(ff)
+    d = big[3:3 + (1 << 20) + 77]
+    assert lib.crc32(d, value=12345) == zlib.crc32(d, 12345)
+    assert lib.adler32(d) == zlib.adler32(d)
+    # both registers in one pass (raw container with ZSTRM_DOCRC | ZSTRM_DOADLER)
+    from jdeflate_b200 import api
+    from test_zstrm import compress
+    d = big[11:11 + (1 << 20) + 300]
+    _, (crc, adler, total) = compress(lib, d, api.ZSTRM_DFLT, piece=len(d), flags=api.ZSTRM_DOCRC | api.ZSTRM_DOADLER)
+    assert (crc, adler, total) == (zlib.crc32(d), zlib.adler32(d), len(d))
