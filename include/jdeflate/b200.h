@@ -3,8 +3,8 @@
  *
  * Nothing here exists in the reference; nothing in the reference API changes.
  * These calls express what the single-stream, synchronous jdeflate API cannot
- * (last row): decoding a batch of independent streams in
- * one launch, and choosing the CUDA device.
+ * (last row): decoding or encoding a batch of independent
+ * streams in one launch, and choosing the CUDA device.
  *
  * All pointers may be host or device (cudaMalloc) addresses; device-resident
  * arguments are used in place, host ones are staged.
@@ -58,6 +58,24 @@ JDEFLATE_API
 int jdb200_inflate_batch(const uint8* source, uint8* target,
                          const TJDB200Item* items, TJDB200Result* results,
                          uintxx count, eJDB200Format format);
+
+/*
+ * Compress `count` independent records, each into a complete stream of its own
+ * (raw DEFLATE, or zlib with header and Adler-32 trailer), in one pass of the
+ * chunk-parallel encoder per group of records -- what the reference does as a loop
+ * of deflator_reset + deflator_setsrc + deflator_deflate(DEFLT_END)
+ * (jdeflate/deflator.h:104-153) plus the zlib framing of zstrm (src/zstrm.c:1033-1110).
+ * Item i is read from source[srcoffset, +srcsize) and written to
+ * target[tgtoffset, +tgtsize).  Results: `status` DEFLT_OK with `srcused` = srcsize and
+ * `tgtused` = bytes written, or DEFLT_TGTEXHSTD when the stream does not fit tgtsize
+ * (nothing is written, srcused = tgtused = 0; srcsize + srcsize / 64 + 80 always fits);
+ * `checksum` is the Adler-32 of the record for JDB200_ZLIB.  `level` as deflator_create.
+ * Returns 0 when the batch ran, non-zero for a runtime failure.
+ */
+JDEFLATE_API
+int jdb200_deflate_batch(const uint8* source, uint8* target,
+                         const TJDB200Item* items, TJDB200Result* results,
+                         uintxx count, eJDB200Format format, intxx level);
 
 /* CUDA device used by instances created afterwards by this thread's process
  * (default: $JDB200_DEVICE, else $LOCAL_RANK, else 0) */

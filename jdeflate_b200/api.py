@@ -161,6 +161,7 @@ class JDeflateLib:
 
         # additive B200 entry points (include/jdeflate/b200.h); absent from the reference object
         bind("jdb200_inflate_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int])
+        bind("jdb200_deflate_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_ssize_t])
         bind("jdb200_set_device", C.c_int, [C.c_int])
         bind("jdb200_device_count", C.c_int, [])
         bind("jdb200_last_error", C.c_char_p, [])
@@ -223,6 +224,30 @@ class JDeflateLib:
         rc = self.lib.jdb200_inflate_batch(C.addressof(src), C.addressof(dst), C.addressof(items), C.addressof(res), n, fmt)
         if rc:
             raise RuntimeError(f"jdb200_inflate_batch rc={rc}: {self.lib.jdb200_last_error().decode()}")
+        outs = [dst.raw[items[i].tgtoffset: items[i].tgtoffset + res[i].tgtused] for i in range(n)]
+        return outs, list(res)
+
+    def deflate_batch(self, source, target, items, results, count, fmt=JDB200_RAW, level=6) -> int:
+        """All four arguments are addresses (host or device); see include/jdeflate/b200.h."""
+        return self.lib.jdb200_deflate_batch(_addr(source), _addr(target), _addr(items), _addr(results), count, fmt, level)
+
+    def deflate_batch_bytes(self, records, caps=None, fmt=JDB200_RAW, level=6):
+        """Host convenience: compress a list of byte strings, each into its own stream;
+        returns (streams, results).  ``caps``: target bytes per record (default: always enough)."""
+        n = len(records)
+        items = (BatchItem * n)()
+        so = to = 0
+        for i, r in enumerate(records):
+            cap = caps[i] if caps is not None else len(r) + len(r) // 64 + 80
+            items[i] = BatchItem(so, to, len(r), cap)
+            so += len(r)
+            to += cap
+        src = C.create_string_buffer(b"".join(records), max(so, 1))
+        dst = C.create_string_buffer(max(to, 1))
+        res = (BatchResult * n)()
+        rc = self.lib.jdb200_deflate_batch(C.addressof(src), C.addressof(dst), C.addressof(items), C.addressof(res), n, fmt, level)
+        if rc:
+            raise RuntimeError(f"jdb200_deflate_batch rc={rc}: {self.lib.jdb200_last_error().decode()}")
         outs = [dst.raw[items[i].tgtoffset: items[i].tgtoffset + res[i].tgtused] for i in range(n)]
         return outs, list(res)
 

@@ -28,11 +28,12 @@
 #include "deflate.cuh"
 
 extern "C" int jdb_huffman_blocks(const uint32_t*, const uint32_t*, uint64_t, uint32_t, uint32_t, uint32_t,
-                                  uint32_t, uint32_t, uint32_t, void*, jdb_stream);
+                                  uint32_t, uint32_t, uint32_t, const uint32_t*, void*, jdb_stream);
 extern "C" size_t jdb_blockinfo_bytes(void);
-extern "C" int jdb_pack_layout(void*, void*, uint32_t, uint32_t, uint32_t*, uint64_t, uint64_t*, jdb_stream);
+extern "C" int jdb_pack_layout(void*, void*, uint32_t, uint32_t, uint32_t*, uint64_t, uint64_t*,
+                               const uint32_t*, uint32_t, uint32_t, jdb_stream);
 extern "C" int jdb_pack_blocks(const uint8_t*, const uint32_t*, const uint32_t*, const void*, const void*,
-                               uint32_t, uint32_t, uint32_t, uint32_t*, jdb_stream);
+                               uint32_t, uint32_t, uint32_t, uint32_t*, const uint32_t*, uint32_t, uint32_t, jdb_stream);
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t) 255; }
 
@@ -44,6 +45,7 @@ struct WorkLayout {
 static int plan(uint64_t n, const jdb_deflate_cfg* cfg, WorkLayout* L)
 {
 	if (cfg->chunk_bytes == 0 || cfg->chunk_bytes % SEG || cfg->block_segs == 0 || cfg->block_segs > 16) return JDB_EARG;
+	if (cfg->chunk_len && (n % cfg->chunk_bytes || cfg->dict_region || cfg->chunk_bytes > CHUNK_LEN_MASK)) return JDB_EARG;
 	const uint64_t nseg = (n + SEG - 1) / SEG;
 	const uint64_t nchunks = n ? (n + cfg->chunk_bytes - 1) / cfg->chunk_bytes : 1;
 	const uint32_t spc = cfg->chunk_bytes / SEG;
@@ -60,7 +62,8 @@ static int plan(uint64_t n, const jdb_deflate_cfg* cfg, WorkLayout* L)
 	L->chunks = off;    off += align256((size_t) nchunks * sizeof(ChunkInfo));
 	L->total = off;     off += 256;
 	L->out = off;
-	L->out_cap = align256((size_t) n + (size_t) n / 64 + (size_t) nblocks * 64 + 4096);
+	L->out_cap = align256((size_t) n + (size_t) n / 64 + (size_t) nblocks * 64 + 4096 +
+	                      (cfg->chunk_len ? (size_t) nchunks * (cfg->wrap_head + cfg->wrap_tail) : 0));
 	off += L->out_cap;
 	L->bytes = off;
 	L->nseg = (uint32_t) nseg;
@@ -75,6 +78,15 @@ extern "C" size_t jdb_deflate_workspace_bytes(uint64_t n, const jdb_deflate_cfg*
 	WorkLayout L;
 	if (plan(n, cfg, &L) != JDB_OK) return 0;
 	return L.bytes;
+}
+
+/* the ChunkInfo table (compressed size and output offset of every chunk) inside `work`,
+ * valid once the pipeline has run on the stream; used by records.cu */
+extern "C" const void* jdb_deflate_chunk_table(uint64_t n, const jdb_deflate_cfg* cfg, const void* work)
+{
+	WorkLayout L;
+	if (plan(n, cfg, &L) != JDB_OK) return NULL;
+	return (const uint8_t*) work + L.chunks;
 }
 
 extern "C" int jdb_deflate_run(const uint8_t* in, uint64_t n, const jdb_deflate_cfg* cfg,
@@ -112,18 +124,20 @@ extern "C" int jdb_deflate_run(const uint8_t* in, uint64_t n, const jdb_deflate_
 			while (range > 65536 && (range & 1) == 0 && (range / 2) % SEG == 0 && (n + range - 1) / range < want) range /= 2;
 		}
 		if (range > cfg->chunk_bytes || cfg->chunk_bytes % range || range % SEG) range = cfg->chunk_bytes;
-		r = jdb_lz_chain(in, n, cfg->chunk_bytes, range, prev, s);
+		r = jdb_lz_chain(in, n, cfg->chunk_bytes, range, cfg->chunk_len, prev, s);
 		if (r != JDB_OK) return r;
-		r = jdb_lz_parse(in, n, cfg->chunk_bytes, prev, cfg->good, cfg->nice, cfg->chain, cfg->lazy,
+		r = jdb_lz_parse(in, n, cfg->chunk_bytes, cfg->chunk_len, prev, cfg->good, cfg->nice, cfg->chain, cfg->lazy,
 		                 cfg->dict_region / SEG, cfg->dict_pad, tok, seg_ntok, seg_hist, s);
 		if (r != JDB_OK) return r;
 	}
 	r = jdb_huffman_blocks(seg_ntok, seg_hist, n, cfg->chunk_bytes, cfg->block_segs, L.nblocks,
-	                       cfg->level, cfg->fixedonly, cfg->dict_region / (cfg->block_segs * SEG), blocks, s);
+	                       cfg->level, cfg->fixedonly, cfg->dict_region / (cfg->block_segs * SEG), cfg->chunk_len, blocks, s);
 	if (r != JDB_OK) return r;
-	r = jdb_pack_layout(blocks, chunks, L.nchunks, L.bpc, outw, L.out_cap / 4, total, s);
+	r = jdb_pack_layout(blocks, chunks, L.nchunks, L.bpc, outw, L.out_cap / 4, total,
+	                    cfg->chunk_len, cfg->wrap_head, cfg->wrap_tail, s);
 	if (r != JDB_OK) return r;
-	r = jdb_pack_blocks(in, tok, seg_ntok, blocks, chunks, L.bpc, L.nchunks, cfg->final, outw, s);
+	r = jdb_pack_blocks(in, tok, seg_ntok, blocks, chunks, L.bpc, L.nchunks, cfg->final, outw,
+	                    cfg->chunk_len, cfg->wrap_head, cfg->wrap_tail, s);
 	if (r != JDB_OK) return r;
 	*out = w + L.out;
 	*total_dev = total;

@@ -50,6 +50,26 @@ struct BlockInfo {
 	uint32_t code[NSYM];     /* bit-reversed code | length << 16 */
 };
 
+/*
+ * Ragged chunks (batched compression of independent records, jdb200_deflate_batch):
+ * chunk c occupies the slot [c * chunk_bytes, (c + 1) * chunk_bytes) of the batch but
+ * only the first chunk_len[c] & CHUNK_LEN_MASK bytes are data.  A record is a run of
+ * chunks, all full but the last; CHUNK_FIRST / CHUNK_LAST mark its ends (the last one
+ * closes the record's stream with BFINAL).  chunk_len == NULL is the plain contiguous
+ * batch.
+ */
+#define CHUNK_LEN_MASK 0x0fffffffu
+#define CHUNK_FIRST    0x40000000u
+#define CHUNK_LAST     0x80000000u
+
+static __device__ __forceinline__ uint64_t
+chunk_end(const uint32_t* __restrict__ chunk_len, uint64_t chunk0, uint32_t chunk_bytes, uint64_t n)
+{
+	if (chunk_len) return chunk0 + (chunk_len[chunk0 / chunk_bytes] & CHUNK_LEN_MASK);
+	const uint64_t e = chunk0 + chunk_bytes;
+	return e > n ? n : e;
+}
+
 struct ChunkInfo {
 	uint64_t bytes;          /* compressed size of the chunk */
 	uint64_t offset;         /* exclusive scan: position in the output */

@@ -196,7 +196,8 @@ struct HdrWriter {
 __global__ void __launch_bounds__(HF_THREADS)
 huffman_kernel(const uint32_t* __restrict__ seg_ntok, const uint32_t* __restrict__ seg_hist,
                uint64_t n, uint32_t chunk_bytes, uint32_t block_segs, uint32_t nblocks,
-               uint32_t level, uint32_t fixedonly, uint32_t skip_blocks, BlockInfo* __restrict__ blocks)
+               uint32_t level, uint32_t fixedonly, uint32_t skip_blocks,
+               const uint32_t* __restrict__ chunk_len, BlockInfo* __restrict__ blocks)
 {
 	__shared__ HfSmem smem[HF_WARPS];
 	HfSmem& S = smem[jdb_warp()];
@@ -208,8 +209,7 @@ huffman_kernel(const uint32_t* __restrict__ seg_ntok, const uint32_t* __restrict
 	const uint32_t bpc = (segs_per_chunk + block_segs - 1) / block_segs;      /* blocks per chunk */
 	const uint32_t chunk = b / bpc, k = b % bpc;
 	const uint64_t chunk0 = (uint64_t) chunk * chunk_bytes;
-	uint64_t chunk1 = chunk0 + chunk_bytes;
-	if (chunk1 > n) chunk1 = n;
+	const uint64_t chunk1 = chunk_end(chunk_len, chunk0, chunk_bytes, n);
 	const uint32_t csegs = (uint32_t) ((chunk1 - chunk0 + SEG - 1) / SEG);    /* segments in this chunk */
 	const uint32_t s0 = k * block_segs;
 	uint32_t ns = s0 < csegs ? csegs - s0 : 0;
@@ -387,11 +387,12 @@ huffman_kernel(const uint32_t* __restrict__ seg_ntok, const uint32_t* __restrict
 
 extern "C" int jdb_huffman_blocks(const uint32_t* seg_ntok, const uint32_t* seg_hist, uint64_t n,
                                   uint32_t chunk_bytes, uint32_t block_segs, uint32_t nblocks,
-                                  uint32_t level, uint32_t fixedonly, uint32_t skip_blocks, void* blocks, jdb_stream s)
+                                  uint32_t level, uint32_t fixedonly, uint32_t skip_blocks,
+                                  const uint32_t* chunk_len, void* blocks, jdb_stream s)
 {
 	if (nblocks == 0) return JDB_OK;
 	JDB_LAUNCH(huffman_kernel, dim3((nblocks + HF_WARPS - 1) / HF_WARPS), dim3(HF_THREADS), 0, s,
-	           seg_ntok, seg_hist, n, chunk_bytes, block_segs, nblocks, level, fixedonly, skip_blocks, (BlockInfo*) blocks);
+	           seg_ntok, seg_hist, n, chunk_bytes, block_segs, nblocks, level, fixedonly, skip_blocks, chunk_len, (BlockInfo*) blocks);
 	return jdb_rt_check_launch("huffman_kernel");
 }
 

@@ -169,11 +169,12 @@ int jdb_inflate_chunks(const uint8_t* src_base, uint8_t* dst_base,
 /* links to the previous same-hash position (u16 distance, 0 = none), one per
  * input byte; `range` (divides chunk_bytes) is the work item of one warp */
 int jdb_lz_chain(const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint32_t range,
-                 uint16_t* prev, jdb_stream s);
+                 const uint32_t* chunk_len, uint16_t* prev, jdb_stream s);
 
 /* match search + parse: tokens of segment k at tok[k*JDB_SEG ...), their count
  * in seg_ntok[k], the 320-bin symbol histogram in seg_hist[k*320 ...) */
-int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes, const uint16_t* prev,
+int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
+                 const uint32_t* chunk_len, const uint16_t* prev,
                  uint32_t good, uint32_t nice, uint32_t chain, uint32_t lazy,
                  uint32_t skip_segs, uint32_t hist_min,
                  uint32_t* tok, uint32_t* seg_ntok, uint32_t* seg_hist, jdb_stream s);
@@ -181,7 +182,8 @@ int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes, const uint
 /* per block Huffman code construction + block type choice */
 int jdb_huffman_blocks(const uint32_t* seg_ntok, const uint32_t* seg_hist, uint64_t n,
                        uint32_t chunk_bytes, uint32_t block_segs, uint32_t nblocks,
-                       uint32_t level, uint32_t fixedonly, uint32_t skip_blocks, void* blocks, jdb_stream s);
+                       uint32_t level, uint32_t fixedonly, uint32_t skip_blocks,
+                       const uint32_t* chunk_len, void* blocks, jdb_stream s);
 
 /* ---- whole pipeline (deflate.cu) ---------------------------------------- */
 typedef struct jdb_deflate_cfg {
@@ -197,6 +199,11 @@ typedef struct jdb_deflate_cfg {
 	 * for the first chunk but produce no output; a multiple of the block size */
 	uint32_t dict_region;
 	uint32_t dict_pad;       /* bytes of padding in front of the dictionary          */
+	/* ragged chunks (records, see deflate.cuh): device array of n / chunk_bytes entries,
+	 * or NULL; wrap_head / wrap_tail bytes are left free in the output in front of the
+	 * first / after the last chunk of every record (container header and trailer) */
+	const uint32_t* chunk_len;
+	uint32_t wrap_head, wrap_tail;
 } jdb_deflate_cfg;
 
 size_t jdb_deflate_workspace_bytes(uint64_t n, const jdb_deflate_cfg* cfg);
@@ -208,6 +215,15 @@ size_t jdb_deflate_workspace_bytes(uint64_t n, const jdb_deflate_cfg* cfg);
  */
 int jdb_deflate_run(const uint8_t* in, uint64_t n, const jdb_deflate_cfg* cfg,
                     void* work, uint8_t** out, uint64_t** total_dev, jdb_stream s);
+
+/* ---- batched records (records.cu) ---------------------------------------- */
+size_t jdb_records_workspace_bytes(uint64_t slot_bytes, const jdb_deflate_cfg* cfg);
+int jdb_records_deflate(const uint8_t* src_base, uint8_t* tgt_base,
+                        const jdb_inflate_item* items, jdb_inflate_result* results,
+                        const uint32_t* first_chunk, uint32_t nrec,
+                        uint32_t chunk_base, uint32_t nchunks, uint32_t format,
+                        const jdb_deflate_cfg* cfg, uint8_t* slots, uint32_t* chunk_len,
+                        void* work, jdb_stream s);
 
 #ifdef __cplusplus
 }

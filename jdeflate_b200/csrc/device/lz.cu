@@ -166,7 +166,7 @@ chain_link_block(ChainSmem& S, uint32_t blk, unsigned lane)
 
 __global__ void __launch_bounds__(CH_THREADS)
 chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t range,
-             uint16_t* __restrict__ prev)
+             const uint32_t* __restrict__ chunk_len, uint16_t* __restrict__ prev)
 {
 	JDB_DYN_SMEM(smem_raw);
 	ChainSmem& S = *(ChainSmem*) smem_raw;
@@ -176,8 +176,8 @@ chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, u
 	const uint64_t r0 = (uint64_t) blockIdx.x * range;
 	if (r0 >= n) return;
 	const uint64_t chunk0 = r0 / chunk_bytes * chunk_bytes;
-	uint64_t chunk1 = chunk0 + chunk_bytes;
-	if (chunk1 > n) chunk1 = n;
+	const uint64_t chunk1 = chunk_end(chunk_len, chunk0, chunk_bytes, n);
+	if (r0 >= chunk1) return;                    /* ragged chunk: nothing in this range */
 	uint64_t r1 = r0 + range;
 	if (r1 > chunk1) r1 = chunk1;
 	const uint64_t start = r0 >= chunk0 + WND ? r0 - WND : chunk0;   /* warm-up start, multiple of SEG */
@@ -396,7 +396,7 @@ lz_parse_phase(LzSmem& S, const LzParams& prm, const uint32_t tid, const uint32_
 template <bool ROUNDS>
 __global__ void __launch_bounds__(LZ_THREADS, 1)
 lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
-          const uint16_t* __restrict__ prev, LzParams prm,
+          const uint32_t* __restrict__ chunk_len, const uint16_t* __restrict__ prev, LzParams prm,
           uint32_t* __restrict__ tok, uint32_t* __restrict__ seg_ntok, uint32_t* __restrict__ seg_hist)
 {
 	JDB_DYN_SMEM(smem_raw);
@@ -407,8 +407,8 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 
 	const uint64_t seg0 = (uint64_t) seg * SEG;
 	const uint64_t chunk0 = seg0 / chunk_bytes * chunk_bytes;
-	uint64_t chunk1 = chunk0 + chunk_bytes;
-	if (chunk1 > n) chunk1 = n;
+	const uint64_t chunk1 = chunk_end(chunk_len, chunk0, chunk_bytes, n);
+	if (seg0 >= chunk1) return;                  /* ragged chunk: empty segment slot */
 	uint64_t seg1 = seg0 + SEG;
 	if (seg1 > chunk1) seg1 = chunk1;
 	const uint32_t seg_len = (uint32_t) (seg1 - seg0);
@@ -789,7 +789,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 /* ---- launchers ------------------------------------------------------------- */
 
 extern "C" int jdb_lz_chain(const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint32_t range,
-                            uint16_t* prev, jdb_stream s)
+                            const uint32_t* chunk_len, uint16_t* prev, jdb_stream s)
 {
 	if (n == 0) return JDB_OK;
 	const size_t smem = sizeof(ChainSmem);
@@ -802,11 +802,12 @@ extern "C" int jdb_lz_chain(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
 	}
 #endif
 	const uint64_t items = (n + range - 1) / range;
-	JDB_LAUNCH(chain_kernel, dim3((unsigned) items), dim3(CH_THREADS), smem, s, in, n, chunk_bytes, range, prev);
+	JDB_LAUNCH(chain_kernel, dim3((unsigned) items), dim3(CH_THREADS), smem, s, in, n, chunk_bytes, range, chunk_len, prev);
 	return jdb_rt_check_launch("chain_kernel");
 }
 
-extern "C" int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes, const uint16_t* prev,
+extern "C" int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
+                            const uint32_t* chunk_len, const uint16_t* prev,
                             uint32_t good, uint32_t nice, uint32_t chain, uint32_t lazy,
                             uint32_t skip_segs, uint32_t hist_min,
                             uint32_t* tok, uint32_t* seg_ntok, uint32_t* seg_hist, jdb_stream s)
@@ -834,9 +835,9 @@ extern "C" int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
 	const uint64_t nseg = (n + SEG - 1) / SEG;
 	if (prm.twophase)
 		JDB_LAUNCH((lz_kernel<true>), dim3((unsigned) nseg), dim3(LZ_THREADS), smem, s,
-		           in, n, chunk_bytes, prev, prm, tok, seg_ntok, seg_hist);
+		           in, n, chunk_bytes, chunk_len, prev, prm, tok, seg_ntok, seg_hist);
 	else
 		JDB_LAUNCH((lz_kernel<false>), dim3((unsigned) nseg), dim3(LZ_THREADS), smem, s,
-		           in, n, chunk_bytes, prev, prm, tok, seg_ntok, seg_hist);
+		           in, n, chunk_bytes, chunk_len, prev, prm, tok, seg_ntok, seg_hist);
 	return jdb_rt_check_launch("lz_kernel");
 }

@@ -38,7 +38,8 @@
 __global__ void __launch_bounds__(1024)
 layout_kernel(BlockInfo* __restrict__ blocks, ChunkInfo* __restrict__ chunks,
               uint32_t nchunks, uint32_t bpc, uint32_t* __restrict__ out_words,
-              uint64_t out_cap_words, uint64_t* __restrict__ total_out)
+              uint64_t out_cap_words, uint64_t* __restrict__ total_out,
+              const uint32_t* __restrict__ chunk_len, uint32_t wrap_head, uint32_t wrap_tail)
 {
 	__shared__ uint64_t warp_sum[32];
 	__shared__ uint64_t carry;
@@ -46,7 +47,9 @@ layout_kernel(BlockInfo* __restrict__ blocks, ChunkInfo* __restrict__ chunks,
 
 	/* phase 1: bit offsets inside every chunk */
 	for (uint32_t c = tid; c < nchunks; c += 1024) {
-		uint64_t cur = 0;
+		const uint32_t cl = chunk_len ? chunk_len[c] : 0u;
+		/* the container header of a record sits in front of its first chunk */
+		uint64_t cur = (cl & CHUNK_FIRST) ? (uint64_t) wrap_head * 8 : 0;
 		for (uint32_t k = 0; k < bpc; k++) {
 			BlockInfo& B = blocks[(uint64_t) c * bpc + k];
 			if (B.nsegs == 0) continue;
@@ -68,6 +71,7 @@ layout_kernel(BlockInfo* __restrict__ blocks, ChunkInfo* __restrict__ chunks,
 		cur += 3;
 		cur = (cur + 7) & ~(uint64_t) 7;
 		cur += 32;
+		if (cl & CHUNK_LAST) cur += (uint64_t) wrap_tail * 8;
 		chunks[c].bytes = cur >> 3;
 	}
 	if (tid == 0) carry = 0;
@@ -116,6 +120,9 @@ layout_kernel(BlockInfo* __restrict__ blocks, ChunkInfo* __restrict__ chunks,
 		/* the marker of a chunk may straddle into the next word */
 		const uint64_t endw = ((chunks[c].offset + chunks[c].bytes) * 8) >> 5;
 		if (endw < out_cap_words) out_words[endw] = 0;
+		/* with a container trailer behind it the marker ends in a word of its own */
+		if (chunk_len && (chunk_len[c] & CHUNK_LAST) && wrap_tail)
+			out_words[((chunks[c].offset + chunks[c].bytes - wrap_tail) * 8) >> 5] = 0;
 	}
 }
 
@@ -190,7 +197,8 @@ __global__ void __launch_bounds__(PK_THREADS)
 pack_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok,
             const uint32_t* __restrict__ seg_ntok, const BlockInfo* __restrict__ blocks,
             const ChunkInfo* __restrict__ chunks, uint32_t bpc, uint32_t nchunks,
-            uint32_t final_stream, uint32_t* __restrict__ out_words)
+            uint32_t final_stream, uint32_t* __restrict__ out_words,
+            const uint32_t* __restrict__ chunk_len, uint32_t wrap_head, uint32_t wrap_tail)
 {
 	__shared__ PkSmem S;
 	const uint32_t tid = threadIdx.x;
@@ -200,11 +208,14 @@ pack_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok,
 	uint8_t* out8 = (uint8_t*) out_words;
 
 	/* a chunk without blocks (empty input): its first slot writes the marker */
-	const bool empty_chunk_marker = B.nsegs == 0 && (b % bpc) == 0 && chunks[chunk].bytes == 5;
+	const uint32_t cl = chunk_len ? chunk_len[chunk] : 0u;
+	const uint32_t lead = (cl & CHUNK_FIRST) ? wrap_head : 0u;
+	const uint32_t trail = (cl & CHUNK_LAST) ? wrap_tail : 0u;
+	const bool empty_chunk_marker = B.nsegs == 0 && (b % bpc) == 0 && chunks[chunk].bytes == 5 + lead + trail;
 	if (B.nsegs == 0 && !empty_chunk_marker) return;
 
-	const uint64_t bit0 = chunks[chunk].offset * 8 + (B.nsegs ? B.bit_off : 0);
-	const bool final_marker = final_stream && chunk == nchunks - 1;
+	const uint64_t bit0 = chunks[chunk].offset * 8 + (B.nsegs ? B.bit_off : (uint64_t) lead * 8);
+	const bool final_marker = chunk_len ? (cl & CHUNK_LAST) != 0 : (final_stream && chunk == nchunks - 1);
 
 	if (B.nsegs == 0) {
 		if (tid == 0) {
@@ -324,20 +335,23 @@ pack_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok,
 /* ---- launchers -------------------------------------------------------------- */
 
 extern "C" int jdb_pack_layout(void* blocks, void* chunks, uint32_t nchunks, uint32_t bpc,
-                               uint32_t* out_words, uint64_t out_cap_words, uint64_t* total_out, jdb_stream s)
+                               uint32_t* out_words, uint64_t out_cap_words, uint64_t* total_out,
+                               const uint32_t* chunk_len, uint32_t wrap_head, uint32_t wrap_tail, jdb_stream s)
 {
 	JDB_LAUNCH(layout_kernel, dim3(1), dim3(1024), 0, s, (BlockInfo*) blocks, (ChunkInfo*) chunks,
-	           nchunks, bpc, out_words, out_cap_words, total_out);
+	           nchunks, bpc, out_words, out_cap_words, total_out, chunk_len, wrap_head, wrap_tail);
 	return jdb_rt_check_launch("layout_kernel");
 }
 
 extern "C" int jdb_pack_blocks(const uint8_t* in, const uint32_t* tok, const uint32_t* seg_ntok,
                                const void* blocks, const void* chunks, uint32_t bpc, uint32_t nchunks,
-                               uint32_t final_stream, uint32_t* out_words, jdb_stream s)
+                               uint32_t final_stream, uint32_t* out_words,
+                               const uint32_t* chunk_len, uint32_t wrap_head, uint32_t wrap_tail, jdb_stream s)
 {
 	const uint64_t nblocks = (uint64_t) nchunks * bpc;
 	if (nblocks == 0) return JDB_OK;
 	JDB_LAUNCH(pack_kernel, dim3((unsigned) nblocks), dim3(PK_THREADS), 0, s, in, tok, seg_ntok,
-	           (const BlockInfo*) blocks, (const ChunkInfo*) chunks, bpc, nchunks, final_stream, out_words);
+	           (const BlockInfo*) blocks, (const ChunkInfo*) chunks, bpc, nchunks, final_stream, out_words,
+	           chunk_len, wrap_head, wrap_tail);
 	return jdb_rt_check_launch("pack_kernel");
 }

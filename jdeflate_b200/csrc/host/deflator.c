@@ -102,20 +102,7 @@ typedef char jdb_deflator_layout_check[(sizeof(struct TDeflator) == sizeof(struc
 #define PRVT ((struct TDEFLTPrvt*) state)
 #define PBLC ((struct TDEFLTPblc*) state)
 
-/* level -> (good, nice, chain), lazy for 6..9: src/deflator.c:241-263 */
-static void
-set_level(jdb_deflate_cfg* cfg, int level)
-{
-	static const uint16_t t[10][3] = {
-		{0, 0, 0}, {8, 4, 2}, {8, 8, 8}, {8, 16, 16}, {8, 32, 32}, {8, 64, 128},
-		{16, 16, 48}, {32, 64, 128}, {64, 128, 320}, {192, 256, 512}
-	};
-	cfg->level = (uint32_t) level;
-	cfg->good = t[level][0];
-	cfg->nice = t[level][1];
-	cfg->chain = t[level][2];
-	cfg->lazy = level >= 6;
-}
+#define set_level jdb_level_params
 
 static size_t
 env_size(const char* name, size_t dflt)

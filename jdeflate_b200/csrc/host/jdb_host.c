@@ -33,6 +33,20 @@ jdb_dbuf_release(jdb_dbuf* b)
 }
 
 void
+jdb_level_params(jdb_deflate_cfg* cfg, int level)
+{
+	static const uint16_t t[10][3] = {
+		{0, 0, 0}, {8, 4, 2}, {8, 8, 8}, {8, 16, 16}, {8, 32, 32}, {8, 64, 128},
+		{16, 16, 48}, {32, 64, 128}, {64, 128, 320}, {192, 256, 512}
+	};
+	cfg->level = (uint32_t) level;
+	cfg->good = t[level][0];
+	cfg->nice = t[level][1];
+	cfg->chain = t[level][2];
+	cfg->lazy = level >= 6;
+}
+
+void
 jdb_fatal(const char* what)
 {
 	fprintf(stderr, "jdeflate-b200: fatal: %s (%s)\n", what, jdb_rt_last_error());

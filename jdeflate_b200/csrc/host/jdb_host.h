@@ -21,6 +21,9 @@ typedef struct {
 int  jdb_dbuf_reserve(jdb_dbuf* b, size_t bytes);
 void jdb_dbuf_release(jdb_dbuf* b);
 
+/* level -> (good, nice, chain), lazy for 6..9: reference setparameters(), src/deflator.c:241-263 */
+void jdb_level_params(jdb_deflate_cfg* cfg, int level);
+
 /* loud failure used where the public API has no error channel */
 void jdb_fatal(const char* what);
 

@@ -204,3 +204,57 @@ def test_preset_dictionary(lib, corpus):
         assert zlib.decompress(de.run(b"hello"), -15) == b"hello"
     finally:
         de.close()
+
+
+def test_batch_api_records(lib, oracle, corpus, monkeypatch):
+    """jdb200_deflate_batch: every record becomes a complete stream of its own --
+    what the reference produces with deflator_reset + deflator_deflate(DEFLT_END) per record.  Each
+    stream must decode through zlib, the oracle and our own batched inflate; sizes stay within 3 % of
+    the reference's per-record streams (levels 6, 9), and results carry the reference's status codes."""
+    recs = ([corpus.json_record(i)[:1500 + 37 * i] for i in range(40)] +
+            [b"", b"x", b"ab" * 9, corpus.fill(0, 40000, offset=5), corpus.fill(3, 20000), b"a" * 70000,
+             corpus.fill(2, 16384), corpus.fill(1, 16385), corpus.fill(5, 32768, offset=(4 << 20) - 9000)])
+    for fmt in (api.JDB200_ZLIB, api.JDB200_RAW):
+        for level in (0, 1, 6, 9):
+            outs, res = lib.deflate_batch_bytes(recs, fmt=fmt, level=level)
+            for r, z, q in zip(recs, outs, res):
+                assert (q.status, q.error, q.zerror) == (api.OK, 0, 0), (fmt, level, len(r))
+                assert (q.srcused, q.tgtused) == (len(r), len(z))
+                if fmt == api.JDB200_ZLIB:
+                    assert zlib.decompress(z) == r
+                    assert q.checksum == zlib.adler32(r) and (z[0] << 8 | z[1]) % 31 == 0
+                    raw = z[2:-4]
+                else:
+                    assert zlib.decompress(z, -15) == r
+                    raw = z
+                st = oracle.inflate(raw + b"\x99", len(r) + 1)
+                assert (st[0], st[1], st[2], st[3]) == (api.OK, 0, r, len(raw)), (fmt, level, len(r))
+            if fmt == api.JDB200_RAW and level in (6, 9):
+                ours = sum(len(z) for z in outs)
+                ref = sum(len(oracle.deflate(r, level)) for r in recs)
+                assert ours <= ref * 1.03, (level, ours, ref)
+            # and back through the batched inflate
+            back, bres = lib.inflate_batch_bytes(outs, [len(r) for r in recs], fmt=fmt)
+            assert back == recs and all(b.status == api.OK and b.zerror == 0 for b in bres)
+    # target ranges that are too small: DEFLT_TGTEXHSTD for those records only
+    caps = [len(r) + len(r) // 64 + 80 for r in recs]
+    caps[3] = 10
+    caps[43] = 100
+    outs, res = lib.deflate_batch_bytes(recs, caps=caps, fmt=api.JDB200_ZLIB, level=6)
+    for i, (r, z, q) in enumerate(zip(recs, outs, res)):
+        if i in (3, 43):
+            assert (q.status, q.srcused, q.tgtused) == (api.TGTEXHSTD, 0, 0)
+        else:
+            assert q.status == api.OK and zlib.decompress(z) == r
+    # several groups (slot budget of 1 MiB) and a forced slot size smaller than most records
+    monkeypatch.setenv("JDB200_BATCH_MIB", "1")
+    many = [corpus.fill(4, 3000 + 11 * i, offset=977 * i) for i in range(150)] + [corpus.fill(0, 3 << 20)]
+    outs, res = lib.deflate_batch_bytes(many, fmt=api.JDB200_RAW, level=6)
+    assert all(q.status == api.OK for q in res) and [zlib.decompress(z, -15) for z in outs] == many
+    monkeypatch.setenv("JDB200_RECORD_CHUNK_KIB", "16")
+    outs2, res = lib.deflate_batch_bytes(many[:20] + [many[-1][:200000]], fmt=api.JDB200_ZLIB, level=1)
+    assert [zlib.decompress(z) for z in outs2] == many[:20] + [many[-1][:200000]]
+    # argument errors
+    assert lib.lib.jdb200_deflate_batch(None, None, None, None, 3, api.JDB200_RAW, 6) != 0
+    assert lib.lib.jdb200_deflate_batch(b"x", b"y", b"z" * 32, b"w" * 32, 1, api.JDB200_RAW, 10) != 0
+    assert lib.lib.jdb200_deflate_batch(None, None, None, None, 0, api.JDB200_RAW, 6) == 0
