@@ -422,7 +422,9 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 		uint4* dst = (uint4*) S.data;
 		const uint32_t nv = nbytes / 16;
 		for (uint32_t i = tid; i < nv; i += LZ_THREADS) dst[i] = __ldg(src + i);
-		for (uint32_t i = nv * 16 + tid; i < DATA_BYTES; i += LZ_THREADS)
+		/* tail bytes, then zeros as far as a comparison can look past the data (320 guard) */
+		const uint32_t fill_end = nv * 16 + 16 + 320 < DATA_BYTES ? nv * 16 + 16 + 320 : DATA_BYTES;
+		for (uint32_t i = nv * 16 + tid; i < fill_end; i += LZ_THREADS)
 			S.data[i] = i < nbytes ? in[hist0 + i] : 0;
 		/* links are staged as absolute shared-memory positions (0xffff = none), so a
 		 * chain step is one load and one range check */
@@ -540,7 +542,11 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 		uint32_t mode = M_FETCH;
 		uint32_t p = 0xffffffffu, j = 0, jmin = 0, maxlen = 0, best = 0, bestd = 0, cur = 0, steps = 0, cb = 0;
 		uint32_t cq = 0, clen = 0, dmax = 0;
-		/* positions are handed out in blocks of LZ_GRAB per warp */
+		/* positions are handed out in blocks of LZ_GRAB per warp; a short segment (a small
+		 * record of a batch) in blocks of 32 so that all warps get some, and only up to
+		 * its end */
+		const uint32_t grab = seg_len >= SEG / 2 ? LZ_GRAB : 32u;
+		const uint32_t slim = (seg_len + LZ_GRAB - 1) & ~(LZ_GRAB - 1);
 		uint32_t wnext = 0, wend = 0;
 		for (;;) {
 			/* a few chain steps per round amortise the phase bookkeeping below; a lane
@@ -597,14 +603,14 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 			if (fetchers) {
 				/* FETCH: positions come from the warp's own range; the counter lives in a
 				 * register (the phase is warp-synchronous), ranks from the ballot */
-				if (wnext == wend && wend < SEG) {
+				if (wnext == wend && wend < slim) {
 					/* the warp's block is used up: take the next LZ_GRAB positions of the
 					 * segment (one shared-memory atomic per block keeps the warps level) */
 					uint32_t g = 0;
-					if (lane == 0) g = atomicAdd(&S.next_pos, LZ_GRAB);
+					if (lane == 0) g = atomicAdd(&S.next_pos, grab);
 					g = __shfl_sync(JDB_FULL_MASK, g, 0);
-					wnext = g < SEG ? g : SEG;
-					wend = g < SEG ? g + LZ_GRAB : SEG;
+					wnext = g < slim ? g : slim;
+					wend = g < slim ? g + grab : slim;
 				}
 				if (ROUNDS) {
 				/* the next positions that need a search: set bits of the need bitmap from
@@ -628,7 +634,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 					p = rank < have ? wbase + (uint32_t) __fns(nbits, 0, (int) rank + 1) : 0xffffffffu;
 					if (rank >= have) {
 						/* nothing (more) in this word / block: next round, or done when the segment is */
-						if (wnext >= wend && wend >= SEG) mode = M_DONE;
+						if (wnext >= wend && wend >= slim) mode = M_DONE;
 					}
 					else if (p >= seg_len || seg_len - p < MINLEN) {
 						/* nothing to find here; stay in FETCH (pass 1 left 0 there) */
@@ -668,7 +674,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 					p = base + rank;
 					if (rank >= have) {
 						/* block exhausted: next round (or done when the segment is) */
-						if (wend >= SEG) mode = M_DONE;
+						if (wend >= slim) mode = M_DONE;
 						p = 0xffffffffu;
 					}
 					else if (p >= seg_len || seg_len - p < MINLEN) {
