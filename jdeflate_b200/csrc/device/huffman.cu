@@ -68,14 +68,14 @@ static __device__ __forceinline__ uint32_t slot_extra(uint32_t s)
 	return dist_extra_bits(s - DSYM0);
 }
 
-/* warp bitonic sort of key[0..512) ascending */
+/* warp bitonic sort of key[0..N) ascending, N a power of two >= 32 */
 static __device__ void
-sort512(uint32_t* key)
+sort_keys(uint32_t* key, uint32_t N)
 {
 	const unsigned lane = jdb_lane();
-	for (uint32_t k = 2; k <= 512; k <<= 1) {
+	for (uint32_t k = 2; k <= N; k <<= 1) {
 		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-			for (uint32_t t = lane; t < 256; t += 32) {
+			for (uint32_t t = lane; t < N / 2; t += 32) {
 				uint32_t i = ((t / j) * (j << 1)) + (t % j);
 				uint32_t l = i + j;
 				uint32_t a = key[i], b = key[l];
@@ -143,17 +143,26 @@ make_lengths(HfSmem& S, uint32_t* freq, uint8_t* len, int n, uint32_t maxlen)
 		else if (used == 1) { if (freq[0]) freq[1] = 1; else freq[0] = 1; }
 	}
 	__syncwarp();
-	for (int i = lane; i < 512; i += 32)
-		S.key[i] = (i < n && freq[i]) ? (freq[i] << 9) | (uint32_t) i : 0xffffffffu;
+	/* only the symbols that occur are sorted: compact their keys, pad to a power of two
+	 * (a small block uses a fraction of the 286 symbols; sorting 512 slots three times per
+	 * block was the larger part of this kernel on batches of small records) */
+	uint32_t nused = 0;
+	for (int i0 = 0; i0 < n; i0 += 32) {
+		const int i = i0 + (int) lane;
+		const bool on = i < n && freq[i] != 0;
+		const unsigned b = __ballot_sync(JDB_FULL_MASK, on);
+		if (on) S.key[nused + __popc(b & ((1u << lane) - 1u))] = (freq[i] << 9) | (uint32_t) i;
+		nused += __popc(b);
+	}
+	uint32_t N = 32;
+	while (N < nused) N <<= 1;
+	for (uint32_t i = nused + lane; i < N; i += 32) S.key[i] = 0xffffffffu;
 	for (int i = lane; i < n; i += 32) len[i] = 0;
 	__syncwarp();
-	sort512(S.key);
+	sort_keys(S.key, N);
 	if (lane == 0) {
-		int used = 0;
-		while (used < n && S.key[used] != 0xffffffffu) {
-			S.work[used] = S.key[used] >> 9;
-			used++;
-		}
+		const int used = (int) nused;
+		for (int i = 0; i < used; i++) S.work[i] = S.key[i] >> 9;
 		mr_lengths(S.work, used);
 		limit_lengths(S.work, used, maxlen);
 		for (int i = 0; i < used; i++) len[S.key[i] & 511u] = (uint8_t) S.work[i];
@@ -161,22 +170,48 @@ make_lengths(HfSmem& S, uint32_t* freq, uint8_t* len, int n, uint32_t maxlen)
 	__syncwarp();
 }
 
-/* canonical codes for len[0..n) -> out[i] = reversed code | len << 16 (lane 0) */
+/* canonical codes for len[0..n) -> out[i] = reversed code | len << 16.  All lanes call:
+ * counts per length by ballots, then every symbol's code is the first code of its length
+ * plus the number of earlier symbols with the same length (32 symbols per step). */
 static __device__ void
 assign_codes(HfSmem& S, const uint8_t* len, int n, uint32_t* out)
 {
-	for (int i = 0; i < 16; i++) S.count[i] = 0;
-	for (int i = 0; i < n; i++) S.count[len[i]]++;
-	S.count[0] = 0;
-	uint32_t c = 0;
-	S.next[0] = 0;
-	for (int l = 1; l <= 15; l++) {
-		c = (c + S.count[l - 1]) << 1;
-		S.next[l] = c;
+	const unsigned lane = jdb_lane();
+	if (lane < 16) S.count[lane] = 0;
+	__syncwarp();
+	for (int i0 = 0; i0 < n; i0 += 32) {
+		const int i = i0 + (int) lane;
+		const uint32_t l = i < n ? len[i] : 0u;
+		for (uint32_t q = 1; q <= 15; q++) {
+			const unsigned b = __ballot_sync(JDB_FULL_MASK, l == q);
+			if (lane == 0 && b) S.count[q] += __popc(b);
+		}
 	}
-	for (int i = 0; i < n; i++) {
-		uint32_t l = len[i];
-		out[i] = l ? rev_bits(S.next[l]++, l) | (l << 16) : 0;
+	__syncwarp();
+	if (lane == 0) {
+		uint32_t c = 0;
+		S.next[0] = 0;
+		for (int l = 1; l <= 15; l++) {
+			c = (c + (l > 1 ? S.count[l - 1] : 0u)) << 1;
+			S.next[l] = c;
+		}
+	}
+	__syncwarp();
+	for (int i0 = 0; i0 < n; i0 += 32) {
+		const int i = i0 + (int) lane;
+		const uint32_t l = i < n ? len[i] : 0u;
+		uint32_t rank = 0, same = 0;
+		for (uint32_t q = 1; q <= 15; q++) {
+			const unsigned b = __ballot_sync(JDB_FULL_MASK, l == q);
+			if (l == q) { rank = __popc(b & ((1u << lane) - 1u)); same = b; }
+		}
+		uint32_t code = 0;
+		if (l) code = S.next[l] + rank;
+		__syncwarp();
+		/* the last lane of every length group moves the group's counter on */
+		if (l && (same >> lane) <= 1u) S.next[l] = code + 1;
+		__syncwarp();
+		if (i < n) out[i] = l ? rev_bits(code, l) | (l << 16) : 0;
 	}
 }
 
@@ -322,10 +357,11 @@ huffman_kernel(const uint32_t* __restrict__ seg_ntok, const uint32_t* __restrict
 		uint8_t* pl = S.plen;
 		make_lengths(S, pf, pl, 19, 7);
 	}
+	assign_codes(S, S.plen, 19, S.work);
+	__syncwarp();
+	if (lane < 19) S.pcode[lane] = (uint16_t) (S.work[lane] & 0xffffu);
+	__syncwarp();
 	if (lane == 0) {
-		uint32_t pc[19];
-		assign_codes(S, S.plen, 19, pc);
-		for (int i = 0; i < 19; i++) S.pcode[i] = (uint16_t) (pc[i] & 0xffffu);
 		int hclen = 19;
 		while (hclen > 4 && S.plen[c_pre_order[hclen - 1]] == 0) hclen--;
 		const int nr = (int) S.red[0], hlit = (int) S.red[1], hdist = (int) S.red[2];
@@ -361,10 +397,8 @@ huffman_kernel(const uint32_t* __restrict__ seg_ntok, const uint32_t* __restrict
 
 	/* 7. publish */
 	if (type == BT_DYNAMIC) {
-		if (lane == 0) {
-			assign_codes(S, S.len, 286, B.code);
-			assign_codes(S, S.len + DSYM0, 30, B.code + DSYM0);
-		}
+		assign_codes(S, S.len, 286, B.code);
+		assign_codes(S, S.len + DSYM0, 30, B.code + DSYM0);
 		for (uint32_t i = lane; i < HDR_WORDS; i += 32) B.hdr[i] = S.hdr[i];
 	} else if (type == BT_FIXED) {
 		for (uint32_t i = lane; i < DSYM0; i += 32) B.code[i] = rev_bits(fixed_code(i), fixed_len(i)) | (fixed_len(i) << 16);

@@ -259,6 +259,7 @@ struct LzParams {
 	uint32_t skip_segs;              /* leading segments that are preset dictionary: history only */
 	uint32_t twophase;               /* full search only where a tentative parse goes */
 	uint32_t hist_min;               /* first byte of the batch a match of chunk 0 may reach (dictionary start) */
+	uint32_t patience;               /* chain steps still allowed once a match has been found */
 };
 
 struct LzSmem {
@@ -593,6 +594,8 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 							bestd = j - cq;
 							cb = S.data[j + best];
 							if (len >= nice || len == maxlen) mode = M_FETCH;
+							/* a match in hand: the rest of the chain gets the reduced budget */
+							if (steps > prm.patience) steps = prm.patience;
 						}
 					} else {
 						clen = len;
@@ -838,6 +841,7 @@ extern "C" int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
 	 * mixed corpus, so it stays off there. */
 	prm.twophase = getenv("JDB_LZ_TWOPHASE") ? (uint32_t) atoi(getenv("JDB_LZ_TWOPHASE")) : (chain >= 128 ? 2u : 0u);
 	prm.short3 = getenv("JDB_LZ_SHORT3") ? (uint32_t) atoi(getenv("JDB_LZ_SHORT3")) : 1u;
+	prm.patience = getenv("JDB_LZ_PATIENCE") ? (uint32_t) atoi(getenv("JDB_LZ_PATIENCE")) : chain;
 	const uint64_t nseg = (n + SEG - 1) / SEG;
 	if (prm.twophase)
 		JDB_LAUNCH((lz_kernel<true>), dim3((unsigned) nseg), dim3(LZ_THREADS), smem, s,
