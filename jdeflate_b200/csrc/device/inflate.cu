@@ -34,15 +34,25 @@
  */
 #include "common.cuh"
 
+#ifndef INF_WARPS
 #define INF_WARPS        16
+#endif
 #define INF_THREADS      (INF_WARPS * 32)
+#ifndef LIT_ROOT
 #define LIT_ROOT         10
+#endif
 #define DIST_ROOT        8
+#ifndef LIT_TABLE
 #define LIT_TABLE        JDB_INF_LIT_TABLE
+#endif
 #define DIST_TABLE       JDB_INF_DIST_TABLE
 #define QUEUE            32
+#ifndef RING
 #define RING             4096u     /* per-warp window of the newest output bytes */
+#endif
+#ifndef MAXBATCH
 #define MAXBATCH         1024u     /* a batch stops growing beyond this many bytes  */
+#endif
 #define RING_KEEP        (RING - MAXBATCH - 258u)
 #define INW              256u      /* words of staged input per warp (1 KiB) */
 

@@ -8,7 +8,8 @@ from jdeflate_b200 import api
 
 n_distinct = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 tile = int(sys.argv[2]) if len(sys.argv) > 2 else 16
-jd = api.load(); c = Corpus()
+import os
+jd = api.load(os.environ.get("JDB200_LIB")); c = Corpus()
 lib = jd.lib
 lib.jdb200_inflate_batch.restype = C.c_int
 lib.jdb200_inflate_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
