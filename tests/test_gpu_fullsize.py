@@ -151,6 +151,58 @@ def test_batched_deflate_quarter_million_records(jd, corpus):
         assert hostb[o:o + n].tobytes() == recs[perm[k]]
 
 
+def test_batch_calls_accept_any_mix_of_host_and_device_pointers(jd, corpus):
+    """include/jdeflate/b200.h: "All pointers may be host or device addresses" -- all 16 residency
+    combinations of (source, target, items, results) for both batch calls, except the documented
+    one that cannot work (host data buffers with a device-only item list in the inflate call)."""
+    import ctypes as C
+    import torch
+    recs = [corpus.json_record(i)[: 800 + 91 * i] for i in range(48)] + [b"", b"q"]
+    n = len(recs)
+    ln = np.array([len(r) for r in recs], np.uint64)
+    caps = ln + ln // np.uint64(64) + np.uint64(80)
+    items = np.zeros((n, 4), np.uint64)
+    items[1:, 0] = np.cumsum(ln)[:-1]
+    items[1:, 1] = np.cumsum(caps)[:-1]
+    items[:, 2] = ln
+    items[:, 3] = caps
+    src_h = np.frombuffer(b"".join(recs), np.uint8).copy()
+    for mask in range(16):
+        dev = [(mask >> k) & 1 for k in range(4)]                      # source, target, items, results
+        tgt_h = np.zeros(int(caps.sum()) + 64, np.uint8)
+        res_h = np.zeros((n, 4), np.uint64)
+        bufs_h = [src_h, tgt_h, items.copy(), res_h]
+        bufs_d = [torch.from_numpy(b.view(np.uint8).reshape(-1)).cuda() if d else None for b, d in zip(bufs_h, dev)]
+        ptr = [bufs_d[k].data_ptr() if dev[k] else bufs_h[k].ctypes.data for k in range(4)]
+        assert jd.deflate_batch(ptr[0], ptr[1], ptr[2], ptr[3], n, api.JDB200_ZLIB, 6) == 0, mask
+        tgt = bufs_d[1].cpu().numpy() if dev[1] else tgt_h
+        res = (bufs_d[3].cpu().numpy().view(np.uint64).reshape(n, 4) if dev[3] else res_h)
+        assert not res.view(np.uint32).reshape(n, 8)[:, 0].any(), mask
+        used = res[:, 3]
+        for k in range(n):
+            o = int(items[k, 1])
+            assert zlib.decompress(tgt[o:o + int(used[k])].tobytes()) == recs[k], (mask, k)
+        # and back: the streams just made, through jdb200_inflate_batch with the same residency
+        it2 = np.zeros((n, 4), np.uint64)
+        it2[:, 0] = items[:, 1]
+        it2[1:, 1] = np.cumsum(ln)[:-1]
+        it2[:, 2] = used
+        it2[:, 3] = ln
+        if dev[2] and not (dev[0] and dev[1]):
+            continue                                                   # host buffers need a host item list
+        comp_h = np.ascontiguousarray(tgt)
+        back_h = np.zeros(int(ln.sum()) + 64, np.uint8)
+        r2_h = np.zeros((n, 4), np.uint64)
+        b2_h = [comp_h, back_h, it2, r2_h]
+        b2_d = [torch.from_numpy(b.view(np.uint8).reshape(-1)).cuda() if d else None for b, d in zip(b2_h, dev)]
+        p2 = [b2_d[k].data_ptr() if dev[k] else b2_h[k].ctypes.data for k in range(4)]
+        assert jd.inflate_batch(p2[0], p2[1], p2[2], p2[3], n, api.JDB200_ZLIB) == 0, mask
+        back = b2_d[1].cpu().numpy() if dev[1] else back_h
+        r2 = (b2_d[3].cpu().numpy().view(np.uint64).reshape(n, 4) if dev[3] else r2_h)
+        assert not r2.view(np.uint32).reshape(n, 8)[:, 0].any(), mask
+        assert back[: int(ln.sum())].tobytes() == b"".join(recs), mask
+
+
 @pytest.mark.parametrize("level", [1, 6])
 def test_zstrm_gzip_streaming_8mib_callbacks(jd, corpus, level):
     """BASELINE config 5: gzip through zstrm_deflate in 8 MiB calls, back through zstrm_inflate with
