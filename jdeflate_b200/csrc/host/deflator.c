@@ -77,6 +77,10 @@ struct TDEFLTPrvt {
 
 	jdb_deflate_cfg cfg;
 	size_t batchcap;
+	/* staged (host) input ramps up: the first batch is an eighth of batchcap and every
+	 * launch doubles it, so that the host-to-device copy of the first batch -- which
+	 * nothing can overlap -- is short and the pipeline fills quickly */
+	size_t stagecap;
 
 	/* two batches overlap: while one runs on `stream`, the other one's input is
 	 * gathered (H2D) and the previous one's output is drained (D2H) on `cstream` */
@@ -113,6 +117,16 @@ env_size(const char* name, size_t dflt)
 		if (x) return (size_t) x;
 	}
 	return dflt;
+}
+
+static size_t
+first_stagecap(const struct TDEFLTPrvt* state)
+{
+	size_t chunk = state->cfg.chunk_bytes;
+	size_t cap = state->batchcap / 8 / chunk * chunk;
+	if (cap < chunk) cap = chunk;
+	if (cap > state->batchcap) cap = state->batchcap;
+	return cap;
 }
 
 TDeflator*
@@ -210,6 +224,7 @@ deflator_reset(TDeflator* state)
 	PRVT->fil = 0;
 	PRVT->nfifo = 0;
 	PRVT->drn = -1;
+	PRVT->stagecap = first_stagecap(PRVT);
 	if (PRVT->hchecks) {
 		PRVT->hchecks[0] = 0xffffffffu;
 		PRVT->hchecks[1] = 1u;
@@ -570,7 +585,7 @@ deflator_deflate(TDeflator* state, eDEFLTFlush flush)
 
 			/* 4. gather into the staging batch */
 			if (srcleft) {
-				size_t room = PRVT->batchcap - fs->stagelen;
+				size_t room = PRVT->stagecap > fs->stagelen ? PRVT->stagecap - fs->stagelen : 0;
 				if (srcleft > room) {
 					srcleft = room;
 				}
@@ -591,7 +606,7 @@ deflator_deflate(TDeflator* state, eDEFLTFlush flush)
 
 			/* 5. queue the pipeline when the batch is full or a flush is due */
 			all_in = PBLC->source == PBLC->send;
-			if (fs->stagelen == PRVT->batchcap || (PBLC->flush && all_in)) {
+			if (fs->stagelen >= PRVT->stagecap || (PBLC->flush && all_in)) {
 				int last = PBLC->flush && all_in;
 				if (fs->stage.ptr == NULL && stage_reserve(PRVT, fs, 4096) != 0) {
 					goto L_FAIL;
@@ -603,6 +618,7 @@ deflator_deflate(TDeflator* state, eDEFLTFlush flush)
 					PRVT->closing = 1;
 				}
 				PRVT->fil ^= 1;
+				PRVT->stagecap = PRVT->stagecap * 2 < PRVT->batchcap ? PRVT->stagecap * 2 : PRVT->batchcap;
 				continue;
 			}
 			if (all_in) {
