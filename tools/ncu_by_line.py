@@ -24,7 +24,7 @@ for r in rows[hi+1:]:
 ts=sum(agg.values()); ti=sum(aggi.values())
 src=open('/root/repo/jdeflate_b200/csrc/device/lz.cu').read().split('\n')
 # regions
-regions=[(404,470,"stage"),(470,500,"pass1/rounds setup"),(500,560,"rounds/need"),(560,576,"WALK"),(576,616,"COMPARE+ballots"),(616,720,"FETCH"),(720,760,"short3"),(760,775,"parse call"),(775,830,"emit"),(296,404,"parse_phase")]
+regions=[(404,466,"stage"),(466,552,"pass 1 / rounds setup (ROUNDS only)"),(552,568,"WALK"),(568,606,"COMPARE + mode ballots"),(606,704,"FETCH (position hand-out)"),(704,742,"3-byte probes"),(742,744,"parse call"),(744,830,"token emission"),(296,404,"parse_phase")]
 reg=collections.Counter(); regs=collections.Counter()
 other=0
 for ln,c in aggi.items():
