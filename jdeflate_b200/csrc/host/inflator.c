@@ -22,7 +22,7 @@
 
 #define POISON        0xDEADBEEFu
 #define INQ_BYTES     ((size_t) 32 << 20)     /* compressed bytes per launch (grows for large windows) */
-#define INQ_MAX       ((size_t) 512 << 20)
+#define INQ_MAX       ((size_t) 2048 << 20)   /* one parallel step should see all the chunks of a window: two steps of half a wave each take twice as long */
 #define OUT_BYTES     ((size_t) 64 << 20)     /* staging for host targets      */
 
 /* chunk-parallel decode of one stream (streams cut by sync markers, i.e. ours) */
