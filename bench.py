@@ -580,7 +580,7 @@ def bench_inflate(jd, corpus, args, torch, np, barrier, peak):
     # one large stream of OURS through the plain inflator (chunk-parallel decode)
     own = None
     try:
-        nown = min(args.mib, 512) * MIB
+        nown = args.mib * MIB
         raw = torch.empty(nown, dtype=torch.uint8, pin_memory=True)
         fill_parallel(corpus, MIXED, raw.data_ptr(), nown, offset=0)
         draw = raw.cuda()
