@@ -17,7 +17,7 @@
  *
  * Workspace layout in HBM (n = batch bytes, rounded up to whole segments):
  *   prev      2 B / byte     hash chain links
- *   tok       4 B / byte     tokens, segment k at tok[k * 16384]
+ *   tok       4 B / byte     tokens, segment k at tok[k * 8192]
  *   seg_ntok  4 B / segment
  *   seg_hist  1280 B / segment
  *   blocks    sizeof(BlockInfo) / block
@@ -44,7 +44,8 @@ struct WorkLayout {
 
 static int plan(uint64_t n, const jdb_deflate_cfg* cfg, WorkLayout* L)
 {
-	if (cfg->chunk_bytes == 0 || cfg->chunk_bytes % SEG || cfg->block_segs == 0 || cfg->block_segs > 16) return JDB_EARG;
+	/* a CTA of the LZ kernel takes two consecutive segments of one chunk */
+	if (cfg->chunk_bytes == 0 || cfg->chunk_bytes % (2 * SEG) || cfg->block_segs == 0 || cfg->block_segs > 16) return JDB_EARG;
 	if (cfg->chunk_len && (n % cfg->chunk_bytes || cfg->dict_region || cfg->chunk_bytes > CHUNK_LEN_MASK)) return JDB_EARG;
 	const uint64_t nseg = (n + SEG - 1) / SEG;
 	const uint64_t nchunks = n ? (n + cfg->chunk_bytes - 1) / cfg->chunk_bytes : 1;

@@ -16,8 +16,8 @@
  *   block    one DEFLATE block = up to `block_segs` consecutive segments of a
  *            chunk, one Huffman code set.
  */
-#define SEG            16384u
-#define SEG_SHIFT      14
+#define SEG            8192u
+#define SEG_SHIFT      13
 #define WND            32768u
 #define MINLEN         4u          /* hash-4 chains find matches of >= 4 bytes */
 #define MAXLEN         258u

@@ -164,7 +164,7 @@ int jdb_inflate_chunks(const uint8_t* src_base, uint8_t* dst_base,
                        uint32_t count, uint32_t* counter, jdb_stream s);
 
 /* ---- deflate pipeline stages (lz.cu, huffman.cu, pack.cu) ---------------- */
-#define JDB_SEG 16384u      /* LZ segment: positions per CTA, histogram granule */
+#define JDB_SEG 8192u      /* LZ segment: positions per CTA, histogram granule */
 
 /* links to the previous same-hash position (u16 distance, 0 = none), one per
  * input byte; `range` (divides chunk_bytes) is the work item of one warp */

@@ -182,12 +182,12 @@ jdb200_deflate_batch(const uint8* source, uint8* target,
 	}
 	/* chunk slot: twice the mean record, a power of two between one LZ segment and the
 	 * chunk size of the streaming encoder (longer records span several chunks) */
-	chunk = JDB_SEG;
+	chunk = 2 * JDB_SEG;
 	while (chunk < DB_MAX_CHUNK && chunk < 2 * (totalbytes / count)) chunk *= 2;
 	{
 		const char* e = getenv("JDB200_RECORD_CHUNK_KIB");
-		if (e && atoi(e) > 0) chunk = ((size_t) atoi(e) << 10) / JDB_SEG * JDB_SEG;
-		if (chunk < JDB_SEG) chunk = JDB_SEG;
+		if (e && atoi(e) > 0) chunk = ((size_t) atoi(e) << 10) / (2 * JDB_SEG) * (2 * JDB_SEG);
+		if (chunk < 2 * JDB_SEG) chunk = 2 * JDB_SEG;
 	}
 	budget = DB_GROUP_BYTES;
 	{
@@ -207,7 +207,7 @@ jdb200_deflate_batch(const uint8* source, uint8* target,
 	memset(&cfg, 0, sizeof cfg);
 	jdb_level_params(&cfg, (int) level);
 	cfg.chunk_bytes = (uint32_t) chunk;
-	cfg.block_segs = 4;
+	cfg.block_segs = 8;
 
 	if (hostsrc) {
 		if (jdb_dbuf_reserve(&bt.src, (size_t) srcspan + 16) != 0) { r = JDB_ENOMEM; goto L_DONE; }

@@ -31,7 +31,7 @@
  * encode speed; the chunk is also the unit of the parallel decode of one stream (inflator.c), where
  * smaller is faster -- 512 KiB is the balance */
 #define DEFAULT_CHUNK   ((size_t) 512 << 10)
-#define DEFAULT_BLOCKSEGS 4
+#define DEFAULT_BLOCKSEGS 8
 
 struct TDEFLTPblc {
 	uint32 state;
@@ -155,7 +155,7 @@ deflator_create(uintxx flags, intxx level, const TAllocator* allctr)
 
 	set_level(&PRVT->cfg, (int) level);
 	chunk = env_size("JDB200_CHUNK_KIB", DEFAULT_CHUNK >> 10) << 10;
-	chunk = (chunk + JDB_SEG - 1) / JDB_SEG * JDB_SEG;
+	chunk = (chunk + 2 * JDB_SEG - 1) / (2 * JDB_SEG) * (2 * JDB_SEG);      /* an LZ CTA takes two segments of one chunk */
 	PRVT->cfg.chunk_bytes = (uint32_t) chunk;
 	PRVT->cfg.block_segs = (uint32_t) env_size("JDB200_BLOCK_SEGS", DEFAULT_BLOCKSEGS);
 	if (PRVT->cfg.block_segs > 16) PRVT->cfg.block_segs = 16;

@@ -129,6 +129,8 @@ void run_grid(dim3 grid, dim3 block, size_t smem, std::function<void()> body)
 		cta.alive = n;
 		cta.bar_arrived = 0;
 		cta.bar_gen = 0;
+		memset(cta.nb_arrived, 0, sizeof(cta.nb_arrived));
+		memset(cta.nb_gen, 0, sizeof(cta.nb_gen));
 		memset(cta.warps, 0, sizeof(cta.warps));
 		memset(dsmem, 0xcd, smem);
 		for (int i = 0; i < n; i++) {

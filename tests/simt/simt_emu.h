@@ -73,6 +73,8 @@ struct Cta {
 	int      alive;
 	int      bar_arrived;
 	unsigned bar_gen;
+	int      nb_arrived[16];       /* named barriers (bar.sync id, count) */
+	unsigned nb_gen[16];
 	Warp     warps[32];
 	uint3    bid;
 	dim3     bdim, gdim;
@@ -113,6 +115,20 @@ static inline void __syncthreads()
 		return;
 	}
 	while (c->bar_gen == gen)
+		simt::yield();
+}
+
+/* bar.sync id, count: `count` threads of the CTA meet at named barrier `id` */
+static inline void simt_named_barrier(unsigned id, int count)
+{
+	simt::Cta* c = simt::g_cta;
+	unsigned gen = c->nb_gen[id];
+	if (++c->nb_arrived[id] >= count) {
+		c->nb_arrived[id] = 0;
+		c->nb_gen[id]++;
+		return;
+	}
+	while (c->nb_gen[id] == gen)
 		simt::yield();
 }
 
