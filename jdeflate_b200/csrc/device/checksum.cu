@@ -482,8 +482,12 @@ ck_combine_kernel(const uint8_t* data, uint32_t nhead, uint64_t nbody, uint32_t 
 /* smallest body that takes the wide kernel (its 128 KiB table fill has to pay) */
 static uint64_t ckw_min_bytes(void)
 {
-	const char* e = getenv("JDB200_CK_WIDE_MIN_KIB");
-	return e && atoll(e) > 0 ? (uint64_t) atoll(e) << 10 : (uint64_t) 16 << 20;
+	/* read once per process */
+	static const uint64_t v = [] {
+		const char* e = getenv("JDB200_CK_WIDE_MIN_KIB");
+		return e && atoll(e) > 0 ? (uint64_t) atoll(e) << 10 : (uint64_t) 16 << 20;
+	}();
+	return v;
 }
 
 extern "C" size_t jdb_checksum_workspace_bytes(void)
@@ -508,17 +512,9 @@ extern "C" int jdb_checksum(const uint8_t* data, size_t n, int which,
 	uint32_t nctas = 0;
 	if (nvec && nbody >= ckw_min_bytes()) {
 		/* one CTA per SM, at least 128 KiB each */
-		static int attr_done[64];
-		int dev = jdb_rt_get_device();
-		if (dev < 0 || dev >= 64) dev = 0;
-#ifndef JDB_SIMT_EMU
-		if (!attr_done[dev]) {
-			cudaFuncSetAttribute(ck_wide_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CKW_SMEM);
-			cudaFuncSetAttribute(ck_wide_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CKW_SMEM);
-			cudaFuncSetAttribute(ck_wide_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CKW_SMEM);
-			attr_done[dev] = 1;
-		}
-#endif
+		JDB_CONFIGURE_SMEM((ck_wide_kernel<true, false>), CKW_SMEM);
+		JDB_CONFIGURE_SMEM((ck_wide_kernel<true, true>), CKW_SMEM);
+		JDB_CONFIGURE_SMEM((ck_wide_kernel<false, true>), CKW_SMEM);
 		uint64_t want = nbody >> 17;
 		uint64_t cap = (uint64_t) jdb_rt_sm_count();
 		nctas = (uint32_t) (want < cap ? want : cap);

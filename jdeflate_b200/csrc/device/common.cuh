@@ -8,6 +8,7 @@
 #ifdef JDB_SIMT_EMU
 	/* CPU debugging build, see tests/simt/simt_emu.h (test infrastructure) */
 	#include "simt_emu.h"
+	#define JDB_CONFIGURE_SMEM(kernel, bytes) do { } while (0)
 #else
 	#include <cuda_runtime.h>
 	/* every kernel launch of the library goes through here: launches are counted
@@ -15,11 +16,24 @@
 	 * events on the launching stream */
 	#define JDB_LAUNCH(kernel, grid, block, smem, stream, ...) \
 		do { \
-			int jdb_prof_slot_ = jdb_prof_begin(#kernel, (stream)); \
+			static int jdb_prof_site_ = -1; \
+			int jdb_prof_slot_ = jdb_prof_begin(#kernel, &jdb_prof_site_, (stream)); \
 			kernel<<<(grid), (block), (smem), (cudaStream_t) (stream)>>>(__VA_ARGS__); \
 			jdb_prof_end(jdb_prof_slot_, (stream)); \
 		} while (0)
 	#define JDB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+	/* opt a kernel in to its dynamic shared memory once per device (the device the calling
+	 * thread is bound to, i.e. the one the launch goes to); idempotent, so a race between two
+	 * threads that both find the flag clear is harmless */
+	#define JDB_CONFIGURE_SMEM(kernel, bytes) \
+		do { \
+			static int jdb_cfg_done_[64]; \
+			const int jdb_cfg_dev_ = jdb_rt_current_device(); \
+			if (jdb_cfg_dev_ >= 0 && jdb_cfg_dev_ < 64 && !__atomic_load_n(&jdb_cfg_done_[jdb_cfg_dev_], __ATOMIC_ACQUIRE)) { \
+				cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (bytes)); \
+				__atomic_store_n(&jdb_cfg_done_[jdb_cfg_dev_], 1, __ATOMIC_RELEASE); \
+			} \
+		} while (0)
 #endif
 
 #include "jdb_device.h"
@@ -29,7 +43,7 @@
 /* set by runtime.cu / runtime_emu.cpp */
 extern "C" int  jdb_rt_check_launch(const char* what);
 extern "C" void jdb_rt_set_error(const char* fmt, ...);
-extern "C" int  jdb_prof_begin(const char* kernel, jdb_stream s);
+extern "C" int  jdb_prof_begin(const char* kernel, int* site, jdb_stream s);
 extern "C" void jdb_prof_end(int slot, jdb_stream s);
 
 static __device__ __forceinline__ unsigned jdb_lane() { return threadIdx.x & 31u; }

@@ -990,14 +990,7 @@ extern "C" int jdb_inflate_batch(const uint8_t* src_base, uint8_t* dst_base,
 	int r = jdb_memset_async(counter, 0, sizeof(uint32_t), s);
 	if (r != JDB_OK) return r;
 	const size_t smem = sizeof(WarpMem) * INF_WARPS;
-#ifndef JDB_SIMT_EMU
-	static int configured[64];
-	int dev = jdb_rt_get_device();
-	if (dev >= 0 && dev < 64 && !configured[dev]) {
-		cudaFuncSetAttribute(inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		configured[dev] = 1;
-	}
-#endif
+	JDB_CONFIGURE_SMEM(inflate_batch_kernel, smem);
 	const uint32_t redo_only = 0;
 	uint32_t ctas = (count + INF_WARPS - 1) / INF_WARPS;
 	uint32_t cap = (uint32_t) jdb_rt_sm_count();
@@ -1068,14 +1061,7 @@ extern "C" int jdb_inflate_chunks(const uint8_t* src_base, uint8_t* dst_base,
 	int r = jdb_memset_async(counter, 0, sizeof(uint32_t), s);
 	if (r != JDB_OK) return r;
 	const size_t smem = sizeof(WarpMem) * INF_WARPS;
-#ifndef JDB_SIMT_EMU
-	static int configured[64];
-	int dev = jdb_rt_get_device();
-	if (dev >= 0 && dev < 64 && !configured[dev]) {
-		cudaFuncSetAttribute(inflate_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		configured[dev] = 1;
-	}
-#endif
+	JDB_CONFIGURE_SMEM(inflate_batch_kernel, smem);
 	uint32_t ctas = (count + INF_WARPS - 1) / INF_WARPS;
 	const uint32_t cap = (uint32_t) jdb_rt_sm_count();
 	if (ctas > cap) ctas = cap;

@@ -31,7 +31,9 @@ int         jdb_rt_init(void);                 /* idempotent */
 const char* jdb_rt_last_error(void);
 int         jdb_rt_sm_count(void);
 int         jdb_rt_set_device(int ordinal);
-int         jdb_rt_get_device(void);
+int         jdb_rt_get_device(void);          /* default device of new instances */
+int         jdb_rt_use_device(int ordinal);   /* bind the calling thread to an instance's device */
+int         jdb_rt_current_device(void);      /* device the calling thread is bound to */
 int         jdb_rt_device_count(void);
 
 /* per-kernel launch counters and (optional) CUDA-event timing */

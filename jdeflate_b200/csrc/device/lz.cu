@@ -1029,14 +1029,7 @@ extern "C" int jdb_lz_chain(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
 {
 	if (n == 0) return JDB_OK;
 	const size_t smem = sizeof(ChainSmem);
-#ifndef JDB_SIMT_EMU
-	static int configured[64];
-	int dev = jdb_rt_get_device();
-	if (dev >= 0 && dev < 64 && !configured[dev]) {
-		cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		configured[dev] = 1;
-	}
-#endif
+	JDB_CONFIGURE_SMEM(chain_kernel, smem);
 	const uint64_t items = (n + range - 1) / range;
 	JDB_LAUNCH(chain_kernel, dim3((unsigned) items), dim3(CH_THREADS), smem, s, in, n, chunk_bytes, range, chunk_len, prev);
 	return jdb_rt_check_launch("chain_kernel");
@@ -1060,16 +1053,9 @@ extern "C" int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
 {
 	if (n == 0) return JDB_OK;
 	const size_t smem = sizeof(LzSmem);
-#ifndef JDB_SIMT_EMU
-	static int configured[64];
-	int dev = jdb_rt_get_device();
-	if (dev >= 0 && dev < 64 && !configured[dev]) {
-		cudaFuncSetAttribute(lz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		configured[dev] = 1;
-#ifdef LZ_PROF
-		atexit(lz_prof_dump);
-#endif
-	}
+	JDB_CONFIGURE_SMEM(lz_kernel, smem);
+#if defined(LZ_PROF) && !defined(JDB_SIMT_EMU)
+	{ static int once_; if (!once_) { once_ = 1; atexit(lz_prof_dump); } }
 #endif
 	const LzEnv& env = lz_env();
 	LzParams prm;

@@ -16,6 +16,7 @@ static __thread struct {
 	jdb_dbuf slots, chunklen, firstchunk, work;      /* jdb200_deflate_batch */
 	uint32_t* counter;
 	int ready;
+	int device;                                      /* where stream and buffers live */
 } bt;
 
 static int
@@ -24,8 +25,23 @@ batch_prepare(void)
 	if (jdb_rt_init() != JDB_OK) {
 		return JDB_ENODEV;
 	}
-	if (bt.ready) {
+	if (bt.ready && bt.device == jdb_rt_current_device()) {
 		return JDB_OK;
+	}
+	if (bt.ready) {
+		/* the default device moved (jdb200_set_device): this thread's scratch moves with it */
+		jdb_stream_sync(bt.stream);
+		jdb_stream_destroy(bt.stream);
+		jdb_dbuf_release(&bt.src);
+		jdb_dbuf_release(&bt.dst);
+		jdb_dbuf_release(&bt.items);
+		jdb_dbuf_release(&bt.results);
+		jdb_dbuf_release(&bt.slots);
+		jdb_dbuf_release(&bt.chunklen);
+		jdb_dbuf_release(&bt.firstchunk);
+		jdb_dbuf_release(&bt.work);
+		jdb_dev_free(bt.counter);
+		bt.ready = 0;
 	}
 	if (jdb_stream_create(&bt.stream) != JDB_OK) {
 		return JDB_ECUDA;
@@ -34,6 +50,7 @@ batch_prepare(void)
 	if (bt.counter == NULL) {
 		return JDB_ENOMEM;
 	}
+	bt.device = jdb_rt_current_device();
 	bt.ready = 1;
 	return JDB_OK;
 }

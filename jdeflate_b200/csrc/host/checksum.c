@@ -21,6 +21,7 @@ static __thread struct {
 	uint32_t*  dvals;     /* device: [0] crc, [1] adler */
 	uint32_t*  hvals;     /* pinned mirror              */
 	int        ready;
+	int        device;    /* where stream and buffers live */
 } ck;
 
 static void
@@ -30,7 +31,17 @@ ck_prepare(void)
 		if (jdb_rt_init() != JDB_OK) {
 			jdb_fatal("CUDA runtime lost");
 		}
-		return;
+		if (ck.device == jdb_rt_current_device()) {
+			return;
+		}
+		/* the default device moved (jdb200_set_device): this thread's scratch moves with it */
+		jdb_stream_sync(ck.stream);
+		jdb_stream_destroy(ck.stream);
+		jdb_dbuf_release(&ck.stage);
+		jdb_dbuf_release(&ck.work);
+		jdb_dev_free(ck.dvals);
+		jdb_pinned_free(ck.hvals);
+		ck.ready = 0;
 	}
 	if (jdb_rt_init() != JDB_OK) {
 		jdb_fatal("checksum helpers need a CUDA device");
@@ -46,6 +57,7 @@ ck_prepare(void)
 	if (ck.dvals == NULL || ck.hvals == NULL) {
 		jdb_fatal("out of memory");
 	}
+	ck.device = jdb_rt_current_device();
 	ck.ready = 1;
 }
 

@@ -69,6 +69,7 @@ struct TDEFLTPrvt {
 
 	const TAllocator* allctr;
 	int32  level;
+	int    device;          /* the GPU this instance lives on (default device at creation) */
 	uint32 used;
 	uint32 closed;          /* the marker of the current request has been written */
 	uint32 closing;         /* ... has been launched                               */
@@ -152,6 +153,7 @@ deflator_create(uintxx flags, intxx level, const TAllocator* allctr)
 	memset(state, 0, sizeof(struct TDEFLTPrvt));
 	PRVT->allctr = allctr;
 	PRVT->level = (int32) level;
+	PRVT->device = jdb_rt_current_device();
 
 	set_level(&PRVT->cfg, (int) level);
 	chunk = env_size("JDB200_CHUNK_KIB", DEFAULT_CHUNK >> 10) << 10;
@@ -208,6 +210,7 @@ deflator_reset(TDeflator* state)
 	PRVT->dict_region = 0;
 	PRVT->dict_pad = 0;
 	if (PRVT->stream) {
+		jdb_rt_use_device(PRVT->device);
 		/* nothing of an abandoned request may still be running */
 		jdb_stream_sync(PRVT->stream);
 		jdb_stream_sync(PRVT->cstream);
@@ -286,7 +289,7 @@ deflator_setdctnr(TDeflator* state, const uint8* dict, uintxx size)
 	if (PRVT->level == 0) {
 		return;                 /* stored blocks never reference it (the reference: no-op at level 0) */
 	}
-	if (jdb_rt_init() != JDB_OK) {
+	if (jdb_rt_use_device(PRVT->device) != JDB_OK) {
 		return;
 	}
 	/* the last 32 KiB are what a match can reach */
@@ -329,6 +332,7 @@ jdb_deflator_set_checks(TDeflator* state, int which)
 int
 jdb_deflator_get_checks(TDeflator* state, uint32* crc, uint32* adler)
 {
+	jdb_rt_use_device(PRVT->device);
 	if (jdb_copy_async(PRVT->hchecks, PRVT->dchecks, 8, PRVT->stream) != JDB_OK ||
 	    jdb_stream_sync(PRVT->stream) != JDB_OK) {
 		return -1;
@@ -503,7 +507,7 @@ deflator_deflate(TDeflator* state, eDEFLTFlush flush)
 		PBLC->state = POISON;
 		return DEFLT_ERROR;
 	}
-	if (jdb_rt_init() != JDB_OK) {
+	if (jdb_rt_use_device(PRVT->device) != JDB_OK) {
 		PBLC->error = DEFLT_EBADSTATE;
 		PBLC->state = POISON;
 		return DEFLT_ERROR;

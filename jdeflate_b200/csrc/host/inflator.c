@@ -31,7 +31,7 @@
 #define PAR_MAXFRAG   4096u                   /* chunks decoded per step (slots of par_stride bytes each) */
 #define PAR_STRIDE    ((size_t) 1 << 20)      /* first guess of the slot size: the encoder's largest default chunk */
 #define PAR_STRIDE_MAX ((size_t) 16 << 20)
-#define PAR_AGAIN     0xffu                   /* internal status: a parallel step ran, not at the end */
+#define PAR_SCRATCH_MAX ((size_t) 8 << 30)    /* slots of one step: fewer chunks per step rather than more memory */
 
 struct TINFLTPblc {
 	uint32 state;
@@ -51,6 +51,7 @@ struct TINFLTPrvt {
 	struct TINFLTPblc public;
 
 	const TAllocator* allctr;
+	int    device;          /* the GPU this instance lives on (default device at creation) */
 	uint32 used;
 	uint32 done;            /* device reported the end of the stream */
 
@@ -68,6 +69,15 @@ struct TINFLTPrvt {
 	jdb_dbuf   par_scratch; /* device: one slot per candidate chunk */
 	size_t     par_stride;
 	uint8*     par_host;    /* pinned mirror of the same */
+	/* chunks decoded by the last step that the target has not taken yet: they stay in
+	 * their slots and are handed out as the caller makes room */
+	struct jdb_par_frag { uint32_t slot; uint32_t produced; }* par_frag;
+	uint32 par_nfrag;
+	uint32 par_cur;         /* next fragment to deliver ... */
+	uint32 par_off;         /* ... and how much of it is gone already */
+	uint32 par_fin;         /* the last fragment ends the stream (BFINAL marker) */
+	uint32 par_starved;     /* the step stopped because the input ended inside a chunk */
+	size_t par_seen;        /* queued bytes that step has seen */
 	jdb_dbuf   outbuf;
 
 	jdb_inflate_state* dstate;
@@ -119,6 +129,7 @@ inflator_create(uintxx flags, const TAllocator* allctr)
 	}
 	memset(state, 0, sizeof(struct TINFLTPrvt));
 	PRVT->allctr = allctr;
+	PRVT->device = jdb_rt_current_device();
 
 	if (jdb_stream_create(&PRVT->stream) != JDB_OK) {
 		goto L_FAIL;
@@ -148,6 +159,7 @@ inflator_reset(TInflator* state)
 {
 	CTB_ASSERT(state);
 
+	jdb_rt_use_device(PRVT->device);
 	PBLC->state = 0;
 	PBLC->error = 0;
 	PBLC->finalinput = 0;
@@ -161,6 +173,8 @@ inflator_reset(TInflator* state)
 	PRVT->inqlen = 0;
 	PRVT->par_ok = 1;
 	PRVT->par_total = 0;
+	PRVT->par_nfrag = PRVT->par_cur = PRVT->par_off = PRVT->par_fin = PRVT->par_starved = 0;
+	PRVT->par_seen = 0;
 	if (PRVT->par_stride == 0) {
 		PRVT->par_stride = PAR_STRIDE;
 	}
@@ -194,6 +208,7 @@ inflator_destroy(TInflator* state)
 	jdb_dbuf_release(&PRVT->par_dev);
 	jdb_dbuf_release(&PRVT->par_scratch);
 	jdb_pinned_free(PRVT->par_host);
+	free(PRVT->par_frag);
 	jdb_dbuf_release(&PRVT->ckwork);
 	jdb_dev_free(PRVT->dchecks);
 	jdb_dev_free(PRVT->dstate);
@@ -211,6 +226,7 @@ inflator_setdctnr(TInflator* state, const uint8* dict, uintxx size)
 	uint64_t v[2];
 	CTB_ASSERT(state && dict && size);
 
+	jdb_rt_use_device(PRVT->device);
 	/* only before the first inflate call (src/inflator.c:905-913) */
 	if (PRVT->used) {
 		poison(PRVT, INFLT_EINCORRECTUSE);
@@ -246,6 +262,7 @@ jdb_inflator_get_checks(TInflator* state, uint32* crc, uint32* adler)
 {
 	uint32_t* h = (uint32_t*) (PRVT->pinned + 208);
 
+	jdb_rt_use_device(PRVT->device);
 	if (jdb_copy_async(h, PRVT->dchecks, 8, PRVT->stream) != JDB_OK ||
 	    jdb_stream_sync(PRVT->stream) != JDB_OK) {
 		return -1;
@@ -358,15 +375,16 @@ find_u32(const uint32_t* a, uint32_t n, uint32_t v)
  *      its own slot of a scratch buffer, stopping at the first empty stored
  *      block: a real chunk reports where it ends and how many bytes it decoded
  *      to; false candidates just fail or lead nowhere;
- *   3. follow the chain start -> marker -> marker ... as far as the target has
- *      room, copying every link from its slot to its place in the output.
+ *   3. follow the chain start -> marker -> marker ... : the chunks of the chain are
+ *      the next bytes of the output.  They stay in their slots (par_frag) and
+ *      deliver_pending() hands them to the caller as the target has room.
  * Nothing is assumed about who wrote the stream: a stream without such markers
  * yields an empty chain and the sequential decoder takes over.
  * Returns 1 when it decoded something, 0 when it does not apply, 2 to be called
  * again (slot size raised), -1 on failure.
  */
 static int
-parallel_step(struct TINFLTPrvt* state, uint8* dst, size_t cap, size_t* produced_out, int* finished)
+parallel_step(struct TINFLTPrvt* state)
 {
 	const size_t u32_bytes = ((size_t) PAR_MAXC + 1) * 4, rec_bytes = ((size_t) PAR_MAXC + 1) * 32;
 	const size_t total_bytes = 256 + 2 * u32_bytes + 2 * rec_bytes;
@@ -382,18 +400,23 @@ parallel_step(struct TINFLTPrvt* state, uint8* dst, size_t cap, size_t* produced
 	jdb_inflate_result* d_res;
 	const size_t n = PRVT->inqlen;
 	const size_t pad = PRVT->inqoff & 3u;
-	uint32_t nc, ns, i, k, nfrag;
+	uint32_t nc, ns, i, k, nfrag, maxfrag;
 	uint64_t total, used;
 	int fin = 0;
 
-	*produced_out = 0;
-	*finished = 0;
+	PRVT->par_nfrag = PRVT->par_cur = PRVT->par_off = PRVT->par_fin = PRVT->par_starved = 0;
 	if (n < 5 || n + pad > 0xfffffff0u) {
 		return 0;
 	}
 	if (PRVT->par_host == NULL) {
 		PRVT->par_host = jdb_pinned_alloc(total_bytes);
 		if (PRVT->par_host == NULL) {
+			return -1;
+		}
+	}
+	if (PRVT->par_frag == NULL) {
+		PRVT->par_frag = malloc((size_t) PAR_MAXFRAG * sizeof(*PRVT->par_frag));
+		if (PRVT->par_frag == NULL) {
 			return -1;
 		}
 	}
@@ -430,10 +453,15 @@ parallel_step(struct TINFLTPrvt* state, uint8* dst, size_t cap, size_t* produced
 	/* 2. decode from the start and from every candidate that has input after it, each
 	 * into its own slot of a scratch buffer, stopping at the first marker it reads: one
 	 * pass gives both the sizes and the bytes (a slot too small for its chunk just ends
-	 * the chain there).  Offsets from here on are relative to the first queued byte. */
+	 * the chain there).  Offsets from here on are relative to the first queued byte.
+	 * The slots of one step stay within a memory budget: fewer chunks per step then. */
+	maxfrag = (uint32_t) (PAR_SCRATCH_MAX / PRVT->par_stride);
+	if (maxfrag > PAR_MAXFRAG) {
+		maxfrag = PAR_MAXFRAG;
+	}
 	ns = 0;
 	h_starts[ns++] = 0;
-	for (i = 0; i < nc && ns < PAR_MAXFRAG; i++) {
+	for (i = 0; i < nc && ns < maxfrag; i++) {
 		if (h_ends[i] > pad && h_ends[i] - pad < n) {
 			h_starts[ns++] = (uint32_t) (h_ends[i] - pad);
 		}
@@ -459,8 +487,7 @@ parallel_step(struct TINFLTPrvt* state, uint8* dst, size_t cap, size_t* produced
 		return 2;
 	}
 
-	/* 3. the chain of real chunks, as far as the target has room; every link is copied
-	 * from its slot to its place in the output */
+	/* 3. the chain of real chunks */
 	total = 0;
 	used = 0;
 	nfrag = 0;
@@ -470,15 +497,12 @@ parallel_step(struct TINFLTPrvt* state, uint8* dst, size_t cap, size_t* produced
 		const uint32_t start = h_starts[k];
 		uint64_t next;
 		if (r.status != JDB_INF_ST_MARKER || r.consumed == 0 || r.consumed > n - start) {
+			/* the input ended inside this chunk: more input continues the chain */
+			PRVT->par_starved = (r.status == INFLT_SRCEXHSTD);
 			break;
 		}
-		if (total + r.produced > cap) {
-			break;
-		}
-		if (r.produced &&
-		    jdb_copy_async(dst + total, PRVT->par_scratch.ptr + (size_t) k * PRVT->par_stride, (size_t) r.produced, PRVT->stream) != JDB_OK) {
-			return -1;
-		}
+		PRVT->par_frag[nfrag].slot = k;
+		PRVT->par_frag[nfrag].produced = (uint32_t) r.produced;
 		nfrag++;
 		total += r.produced;
 		used = start + r.consumed;
@@ -488,33 +512,51 @@ parallel_step(struct TINFLTPrvt* state, uint8* dst, size_t cap, size_t* produced
 		}
 		next = start + r.consumed;
 		if (next >= n) {
+			PRVT->par_starved = 1;      /* the queue ends with the marker */
 			break;
 		}
 		i = find_u32(h_starts + k + 1, ns - (k + 1), (uint32_t) next);
 		if (i == ns - (k + 1)) {
-			break;
+			break;                      /* more chunks than slots: the next step goes on from here */
 		}
 		k = k + 1 + i;
 	}
 	if (nfrag == 0) {
+		/* not one whole chunk: an unfinished first chunk of a chain that was already
+		 * under way waits for more input; anything else is not ours to decode */
+		PRVT->par_starved = PRVT->par_starved && PRVT->par_total != 0;
+		PRVT->par_seen = n;
 		return 0;
 	}
 
 	/* the sequential decoder may have to go on from here: leave its state at the
-	 * block boundary after the last chunk, with the newest 32 KiB as history */
+	 * block boundary after the last chunk, with the newest 32 KiB as history
+	 * (gathered from the slots, newest chunk first) */
 	{
 		const uint64_t newtotal = PRVT->par_total + total;
-		uint64_t h = total < JDB_INFLATE_HISTORY ? total : JDB_INFLATE_HISTORY;
-		uint64_t first = newtotal - h;                       /* absolute position of the oldest byte copied */
-		uint64_t head = JDB_INFLATE_HISTORY - (first & (JDB_INFLATE_HISTORY - 1));
+		uint64_t left = total < JDB_INFLATE_HISTORY ? total : JDB_INFLATE_HISTORY;
+		uint64_t end = newtotal;                             /* absolute position after the bytes still to copy */
 		uint64_t* hw = (uint64_t*) (PRVT->pinned + 128);
 		uint32_t* hw32 = (uint32_t*) (PRVT->pinned + 128 + 24);
-		if (head > h) {
-			head = h;
-		}
-		if (jdb_copy_async(PRVT->dstate->history + (first & (JDB_INFLATE_HISTORY - 1)), dst + total - h, (size_t) head, PRVT->stream) != JDB_OK ||
-		    jdb_copy_async(PRVT->dstate->history, dst + total - h + head, (size_t) (h - head), PRVT->stream) != JDB_OK) {
-			return -1;
+		uint32_t f = nfrag;
+		while (left && f) {
+			const struct jdb_par_frag* fr = &PRVT->par_frag[--f];
+			const uint8_t* slot = PRVT->par_scratch.ptr + (size_t) fr->slot * PRVT->par_stride;
+			uint64_t take = fr->produced < left ? fr->produced : left;
+			uint64_t first = end - take;                     /* absolute position of the oldest byte of this piece */
+			const uint8_t* src = slot + (fr->produced - take);
+			uint64_t ring = first & (JDB_INFLATE_HISTORY - 1);
+			uint64_t head = JDB_INFLATE_HISTORY - ring;
+			if (head > take) {
+				head = take;
+			}
+			if (jdb_copy_async(PRVT->dstate->history + ring, src, (size_t) head, PRVT->stream) != JDB_OK ||
+			    (take > head &&
+			     jdb_copy_async(PRVT->dstate->history, src + head, (size_t) (take - head), PRVT->stream) != JDB_OK)) {
+				return -1;
+			}
+			end = first;
+			left -= take;
 		}
 		hw[0] = 0;                                           /* bitbuf */
 		hw[1] = newtotal;                                    /* total_out */
@@ -533,9 +575,76 @@ parallel_step(struct TINFLTPrvt* state, uint8* dst, size_t cap, size_t* produced
 	}
 	PRVT->inqoff += (size_t) used;
 	PRVT->inqlen -= (size_t) used;
-	*produced_out = (size_t) total;
-	*finished = fin;
+	PRVT->par_seen = PRVT->inqlen;
+	PRVT->par_nfrag = nfrag;
+	PRVT->par_fin = (uint32) fin;
 	return 1;
+}
+
+/* 1 when the bytes queued since the last step hold a marker candidate, 0 when not, -1 on failure */
+static int
+new_marker(struct TINFLTPrvt* state)
+{
+	const size_t from = PRVT->par_seen > 3 ? PRVT->par_seen - 3 : 0;       /* a marker may straddle old and new bytes */
+	const size_t off = PRVT->inqoff + from;
+	const size_t pad = off & 3u;
+	uint32_t* h_count = (uint32_t*) PRVT->par_host;
+	uint8_t* d = PRVT->par_dev.ptr;
+
+	if (PRVT->par_host == NULL || d == NULL) {
+		return 1;
+	}
+	if (jdb_marker_scan(PRVT->inq.ptr + off - pad, PRVT->inqlen - from + pad, (uint32_t*) (d + 256), PAR_MAXC,
+	                    (uint32_t*) d, PRVT->stream) != JDB_OK ||
+	    jdb_copy_async(h_count, d, 4, PRVT->stream) != JDB_OK ||
+	    jdb_stream_sync(PRVT->stream) != JDB_OK) {
+		return -1;
+	}
+	PRVT->par_seen = PRVT->inqlen;
+	return h_count[0] != 0;
+}
+
+/*
+ * Hand decoded chunks that wait in their slots to the caller, as far as the target has
+ * room (device target: device copy; host target: straight from the slot).  The running
+ * checksums follow the bytes delivered.  Returns 0, or -1 on failure.
+ */
+static int
+deliver_pending(struct TINFLTPrvt* state)
+{
+	int copied = 0;
+
+	while (PRVT->par_cur < PRVT->par_nfrag && PBLC->target != PBLC->tend) {
+		const struct jdb_par_frag* fr = &PRVT->par_frag[PRVT->par_cur];
+		const uint8_t* src = PRVT->par_scratch.ptr + (size_t) fr->slot * PRVT->par_stride + PRVT->par_off;
+		size_t left = fr->produced - PRVT->par_off;
+		size_t room = (size_t) (PBLC->tend - PBLC->target);
+		size_t take = left < room ? left : room;
+
+		if (take) {
+			if (PRVT->checks) {
+				if (jdb_dbuf_reserve(&PRVT->ckwork, jdb_checksum_workspace_bytes()) != 0 ||
+				    jdb_checksum(src, take, PRVT->checks, PRVT->dchecks, PRVT->dchecks + 1,
+				                 PRVT->ckwork.ptr, PRVT->stream) != JDB_OK) {
+					return -1;
+				}
+			}
+			if (jdb_copy_async(PBLC->target, src, take, PRVT->stream) != JDB_OK) {
+				return -1;
+			}
+			copied = 1;
+			PBLC->target += take;
+		}
+		PRVT->par_off += (uint32) take;
+		if (PRVT->par_off == fr->produced) {
+			PRVT->par_cur++;
+			PRVT->par_off = 0;
+		}
+	}
+	if (copied && jdb_stream_sync(PRVT->stream) != JDB_OK) {
+		return -1;
+	}
+	return 0;
 }
 
 eINFLTResult
@@ -554,7 +663,7 @@ inflator_inflate(TInflator* state, uint32 final)
 		PBLC->state = POISON;
 		return INFLT_ERROR;
 	}
-	if (jdb_rt_init() != JDB_OK) {
+	if (jdb_rt_use_device(PRVT->device) != JDB_OK) {
 		poison(PRVT, INFLT_EBADSTATE);
 		return INFLT_ERROR;
 	}
@@ -564,15 +673,79 @@ inflator_inflate(TInflator* state, uint32 final)
 	for (;;) {
 		jdb_inflate_item* item = H_ITEM(PRVT);
 		jdb_inflate_result* res = H_RESULT(PRVT);
-		uint8* dst;
-		size_t cap;
-		size_t absorbed_all;
+		uint8* dst = NULL;
+		size_t cap = 0;
+		size_t absorbed_all = 0;
+
+		/* chunks of an earlier parallel step that the target had no room for */
+		if (PRVT->par_cur < PRVT->par_nfrag) {
+			if (deliver_pending(PRVT) != 0) {
+				poison(PRVT, INFLT_EBADSTATE);
+				return INFLT_ERROR;
+			}
+			if (PRVT->par_cur < PRVT->par_nfrag) {
+				return (eINFLTResult) (PBLC->status = INFLT_TGTEXHSTD);
+			}
+			if (PRVT->par_fin) {
+				res->status = INFLT_OK;
+				res->error = 0;
+				res->consumed = 0;
+				res->produced = 0;
+				goto L_DELIVER;
+			}
+		}
 
 		if (absorb(PRVT) != 0) {
 			poison(PRVT, INFLT_EOOM);
 			return INFLT_ERROR;
 		}
 		absorbed_all = (PBLC->source == PBLC->send);
+
+		/* a stream cut into chunks by sync markers (ours) is decoded chunk-parallel
+		 * while the decoder sits at a block boundary */
+		if (PRVT->par_ok) {
+			int step = PRVT->inqlen >= PAR_MIN_BYTES ||
+			           (PBLC->finalinput && absorbed_all && PRVT->inqlen >= ((size_t) 256 << 10));
+			if (!step && PRVT->par_starved) {
+				/* a streaming caller with small windows: the last step stopped because the
+				 * queue ended inside a chunk (or right after one).  Nothing new: ask for
+				 * input.  New bytes with a marker among them: the chain may go on.  New
+				 * bytes without one: cannot tell an unfinished chunk from the unmarked end
+				 * of somebody else's stream -- the sequential decoder decides. */
+				if (PRVT->inqlen == PRVT->par_seen) {
+					if (absorbed_all && !PBLC->finalinput) {
+						return (eINFLTResult) (PBLC->status = INFLT_SRCEXHSTD);
+					}
+				}
+				else {
+					int found = new_marker(PRVT);
+					if (found < 0) {
+						poison(PRVT, INFLT_EBADSTATE);
+						return INFLT_ERROR;
+					}
+					step = found;
+				}
+			}
+			if (step) {
+				int pr = parallel_step(PRVT);
+				if (pr < 0) {
+					poison(PRVT, INFLT_EBADSTATE);
+					return INFLT_ERROR;
+				}
+				if (pr == 2) {
+					continue;           /* the slots were too small for the chunks: again with larger ones */
+				}
+				if (pr > 0) {
+					continue;           /* the chunks wait in their slots: the top of the loop delivers them */
+				}
+				if (PRVT->par_starved && absorbed_all && !PBLC->finalinput) {
+					/* still the same unfinished chunk at the head of the queue */
+					return (eINFLTResult) (PBLC->status = INFLT_SRCEXHSTD);
+				}
+			}
+			/* no chain of chunks here: the sequential decoder owns the stream from now on */
+		}
+		PRVT->par_ok = 0;
 
 		cap = (size_t) (PBLC->tend - PBLC->target);
 		if (tgt_on_device) {
@@ -601,35 +774,6 @@ inflator_inflate(TInflator* state, uint32 final)
 			}
 			PRVT->inqcap = INQ_BYTES;
 		}
-
-		/* a stream cut into chunks by sync markers (ours) is decoded chunk-parallel
-		 * while the decoder sits at a block boundary */
-		if (PRVT->par_ok &&
-		    (PRVT->inqlen >= PAR_MIN_BYTES || (PBLC->finalinput && absorbed_all && PRVT->inqlen >= ((size_t) 256 << 10)))) {
-			size_t made = 0;
-			int fin = 0;
-			int pr = parallel_step(PRVT, dst, cap, &made, &fin);
-			if (pr < 0) {
-				poison(PRVT, INFLT_EBADSTATE);
-				return INFLT_ERROR;
-			}
-			if (pr == 2) {
-				continue;               /* the slots were too small for the chunks: again with larger ones */
-			}
-			if (pr > 0) {
-				/* not finished: go round again -- more chunks, or the sequential decoder
-				 * for what follows (it alone decides between "target full", "need input"
-				 * and "stream ended") */
-				res->status = fin ? INFLT_OK : PAR_AGAIN;
-				res->error = 0;
-				res->consumed = 0;              /* the queue was advanced by the step itself */
-				res->produced = made;
-				goto L_DELIVER;
-			}
-			/* no chain of chunks here: the sequential decoder owns the stream from now on */
-			PRVT->par_ok = 0;
-		}
-		PRVT->par_ok = 0;
 
 		if (jdb_copy_async(D_ITEM(PRVT), item, sizeof(*item), PRVT->stream) != JDB_OK ||
 		    jdb_inflate_batch(PRVT->inq.ptr, dst, D_ITEM(PRVT), D_RESULT(PRVT), PRVT->dstate, 1,
@@ -683,15 +827,6 @@ L_DELIVER:
 				PBLC->error = res->error ? res->error : INFLT_EBADSTATE;
 				PBLC->state = POISON;
 				return INFLT_ERROR;
-			case PAR_AGAIN:
-				/* a streaming caller: the queue holds only the beginning of the next
-				 * chunk and more input is coming -- ask for it and stay on the parallel
-				 * path instead of handing the stream to the sequential decoder */
-				if (absorbed_all && !PBLC->finalinput && PBLC->target != PBLC->tend &&
-				    PRVT->inqlen < PAR_MIN_BYTES) {
-					return (eINFLTResult) (PBLC->status = INFLT_SRCEXHSTD);
-				}
-				continue;
 			case INFLT_TGTEXHSTD:
 				if (PBLC->target == PBLC->tend) {
 					return (eINFLTResult) (PBLC->status = INFLT_TGTEXHSTD);

@@ -21,6 +21,8 @@ extern "C" int jdb_rt_sm_count(void) { const char* e = getenv("JDB_EMU_SMS"); re
 extern "C" int jdb_rt_get_device(void) { return 0; }
 extern "C" int jdb_rt_device_count(void) { return 1; }
 extern "C" int jdb_rt_set_device(int) { return JDB_OK; }
+extern "C" int jdb_rt_use_device(int) { return JDB_OK; }
+extern "C" int jdb_rt_current_device(void) { return 0; }
 extern "C" void* jdb_dev_alloc(size_t bytes)
 {
 	if (!bytes) bytes = 16;
@@ -50,7 +52,7 @@ extern "C" int jdb_event_record(jdb_event, jdb_stream) { return JDB_OK; }
 extern "C" int jdb_stream_wait_event(jdb_stream, jdb_event) { return JDB_OK; }
 extern "C" int jdb_event_sync(jdb_event) { return JDB_OK; }
 
-extern "C" int  jdb_prof_begin(const char*, jdb_stream) { return -1; }
+extern "C" int  jdb_prof_begin(const char*, int*, jdb_stream) { return -1; }
 extern "C" void jdb_prof_end(int, jdb_stream) {}
 extern "C" int  jdb_prof_enable(int) { return JDB_OK; }
 extern "C" int  jdb_prof_read(jdb_kernel_stat*, int) { return 0; }

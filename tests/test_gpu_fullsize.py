@@ -271,3 +271,22 @@ def test_zlib_level9_logs_sharded_two_ranks(jd, oracle, corpus):
     ours = len(jd.deflate_bytes(sample, 9))
     ref = len(oracle.deflate(sample, 9))
     assert ours <= 1.03 * ref, (ours, ref)
+
+
+def test_cross_decode_64mib_with_the_compiled_reference(jd, ref, corpus):
+    """A C1-sized slice (64 MiB of text, raw DEFLATE, level 6) both ways through the unmodified
+    reference compiled from its own sources (oracle/_ref): what the GPU encoder emits decodes
+    bit-exactly through the reference's inflator_inflate, what the reference's deflator emits
+    decodes bit-exactly through the GPU inflator, and the sizes are within the 3 % the north star
+    allows."""
+    n = 64 * MIB
+    d = corpus.fill(0, n, offset=9 << 20)
+    ours = jd.deflate_bytes(d, 6)
+    st, err, back, used = ref.inflate_bytes(ours, n)
+    assert (st, err, used) == (api.OK, 0, len(ours))
+    assert back == d
+    theirs = ref.deflate_bytes(d, 6)
+    st, err, back, used = jd.inflate_bytes(theirs, n)
+    assert (st, err, used) == (api.OK, 0, len(theirs))
+    assert back == d
+    assert len(ours) <= 1.03 * len(theirs)

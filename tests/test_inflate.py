@@ -188,3 +188,52 @@ def test_chunk_parallel_decode_of_marker_cut_streams(lib, oracle, corpus, monkey
     assert (got[0], got[1]) == (exp[0], exp[1])
     if exp[0] == api.OK:
         assert got[2] == exp[2]
+
+
+def test_parallel_path_not_final_input(lib, corpus):
+    """Regression (round-1 advice): after a chunk-parallel step the inflator must not ask for more
+    input while the queue still holds the complete rest of the stream.  final = 0 throughout, as
+    zstrm calls it; the reference returns INFLT_OK for the same calls."""
+    d = corpus.fill(0, 4392960, offset=1 << 20)
+    for wbits in (-15, 15, 31):
+        co = zlib.compressobj(6, zlib.DEFLATED, wbits)
+        z = co.compress(d[:307200]) + co.flush(zlib.Z_FULL_FLUSH) + co.compress(d[307200:]) + co.flush()
+        assert len(z) >= 1 << 20
+        if wbits == -15:
+            st, err, out, used = lib.inflate_bytes(z, len(d), final=False)
+            assert (st, err, used) == (api.OK, 0, len(z))
+            assert out == d
+        else:
+            zs = lib.zstrm(api.ZSTRM_INFLATE | (api.ZSTRM_ZLIB if wbits == 15 else api.ZSTRM_GZIP))
+            zs.setsource(z)
+            out = zs.inflate(len(d) + 16)
+            assert zs.error == 0, wbits
+            assert out == d, wbits
+            zs.close()
+
+
+def test_parallel_path_host_target_larger_than_staging(lib, corpus):
+    """Regression (round-1 advice): a chain of chunks longer than what one pass can hand to a host
+    target (64 MiB) is delivered over several passes of the same call -- final = 0, all input given."""
+    n = 66 << 20
+    d = corpus.fill(3, 1 << 20) * 66
+    z = lib.deflate_bytes(d, 0)
+    st, err, out, used = lib.inflate_bytes(z, n, final=False)
+    assert (st, err, used) == (api.OK, 0, len(z))
+    assert len(out) == n and zlib.crc32(out) == zlib.crc32(d)
+    # the same stream through small target windows: the decoded chunks wait in their slots
+    st, err, out, used = lib.inflate_bytes(z[: 9 << 20] , 9 << 20, window=(1 << 20) + 13, final=False)
+    assert st == api.SRCEXHSTD and err == 0
+    assert out == d[: len(out)] and len(out) >= 8 << 20
+
+
+def test_parallel_path_small_source_windows(lib, corpus, monkeypatch):
+    """A streaming caller that feeds our own stream in windows smaller than a parallel step wants:
+    bytes and status as the sequential decoder, whichever path ends up decoding."""
+    monkeypatch.setenv("JDB200_CHUNK_KIB", "64")
+    d = corpus.fill(0, 6 << 20, offset=3 << 20)
+    z = lib.deflate_bytes(d, 6)
+    for feed in (1 << 20, 300000, 65536):
+        st, err, out, used = lib.inflate_bytes(z, len(d), feed=feed, final=False)
+        assert (st, err, used) == (api.OK, 0, len(z)), feed
+        assert out == d, feed
