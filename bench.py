@@ -8,12 +8,17 @@ figure of the same run rides in the "inflate" object of the JSON line.
 
 Workload at N = 1: BASELINE.json configs[1] -- gzip level 6 of 1 GiB of the mixed synthetic
 corpus (4 MiB segments cycling TEXT / BINARY / INCOMPRESSIBLE).  One step = one pass of the hot
-path over that 1 GiB.  At N > 1 every rank compresses its own 1 GiB slice of the corpus (weak
-scaling); the only collective is one all_gather of the per-rank {compressed bytes, crc32, length}
-that fixes the output offsets and the whole-stream CRC.
+path over that 1 GiB.  At N > 1 the job is ONE gzip member of N GiB (weak scaling: 1 GiB per rank):
+rank g compresses the slice jdeflate_b200.shard.plan() gives it, ends with DEFLT_FLUSH (the last
+owner with DEFLT_END), and every step runs the one collective of the path -- an all_gather of the
+per-rank {compressed bytes, crc32, length} that fixes the output offsets and the whole-stream CRC
+(SURVEY.md 8e); after the timed region rank 0 gathers the parts once and decodes the assembled
+member (header + parts + trailer).
 
   value      device-resident: input already in HBM, output to HBM, through the C ABI
-             (deflator_* on device pointers + the gzip CRC-32 of the input)
+             (deflator_* on device pointers, the gzip CRC-32 of the input, the 10-byte header
+             and the 8-byte trailer written around the stream in HBM)
+  c3 / c4 / c5   the other BASELINE configs at their stated sizes (see the functions below)
   e2e        the same work through the reference-facing zstrm API with HOST buffers: pinned input,
              zstrm_deflate(8 MiB pieces) -> target callback; every byte crosses PCIe inside the
              timed region
@@ -150,10 +155,11 @@ def cpu_reference(corpus, op, level, sample_bytes, threads, offset=0):
 
 
 def cpu_sample_size(cores, total):
-    # ~12 MiB of the mixed corpus per core (whole TEXT/BINARY/INCOMP cycles), capped by the workload
-    n = 12 * MIB * max(1, cores)
-    n = max(12 * MIB, min(n, total))
-    return n - n % (12 * MIB) if n >= 12 * MIB else n
+    # >= 2 s of wall time: 60 MiB of the mixed corpus per core (whole TEXT/BINARY/INCOMP cycles of
+    # 12 MiB); the sample may be larger than one GPU step's input -- it is a sample of the same
+    # corpus, and a longer one is a steadier denominator
+    n = 60 * MIB * max(1, cores)
+    return max(12 * MIB, n - n % (12 * MIB))
 
 
 def run_reference_arm(args, real_stdout=sys.stdout):
@@ -198,6 +204,65 @@ def workload_config(args, extra=None):
     return c
 
 
+def verify_sharded(jd, api, torch, np, dist, rank, world, dev_in, dev_out, produced, state, total_bytes, wbits, log,
+                   trailer="crc32"):
+    """After the timed region: rank 0 receives every rank's part once (NCCL send / recv into its place
+    at the gathered offset), so that the assembled container -- header + parts + trailer -- exists
+    in one piece, and decodes it: the whole of it through this library's inflator on the GPU
+    (output checksum against the member checksum the all_gather produced), its head through zlib
+    on the host, and all of it through zlib when it is at most 2 GiB."""
+    t0 = time.time()
+    if world > 1:
+        sizes = torch.tensor([produced], dtype=torch.int64, device="cuda")
+        allsz = [torch.zeros_like(sizes) for _ in range(world)]
+        dist.all_gather(allsz, sizes)
+        allsz = [int(x.item()) for x in allsz]
+        offs = [sum(allsz[:r]) for r in range(world)]
+        total = sum(allsz)
+        if rank != 0:
+            dist.send(dev_out[:produced].contiguous(), dst=0)
+            return None
+        member = torch.empty(total, dtype=torch.uint8, device="cuda")
+        member[:produced].copy_(dev_out[:produced])
+        for r in range(1, world):
+            dist.recv(member[offs[r]:offs[r] + allsz[r]], src=r)
+        torch.cuda.synchronize()
+    else:
+        offs, total, member = [0], produced, dev_out[:produced]
+    head, tail = (10, 8) if wbits == 31 else (2, 4)
+    back = torch.empty(total_bytes, dtype=torch.uint8, device="cuda")
+    si = jd.inflator()
+    si.setsrc(member.data_ptr() + head, total - head - tail)
+    si.settgt(back.data_ptr(), total_bytes)
+    r = si.inflate(1)
+    assert r == api.OK and si.tgtend() == total_bytes and si.srcend() == total - head - tail, (r, si.error, si.tgtend())
+    si.close()
+    tr = member[total - tail:].cpu().numpy().tobytes()
+    if trailer == "crc32":
+        got = jd.lib.zstrm_crc32update(0xFFFFFFFF, back.data_ptr(), total_bytes) ^ 0xFFFFFFFF
+        assert got == state["member_crc"], "sharded member: decoded CRC-32 differs from the combined CRC"
+        assert tr == got.to_bytes(4, "little") + (total_bytes & 0xFFFFFFFF).to_bytes(4, "little"), "gzip trailer"
+    else:
+        got = jd.lib.zstrm_adler32update(1, back.data_ptr(), total_bytes)
+        assert got == state["member_crc"], "sharded stream: decoded Adler-32 differs from the combined Adler-32"
+        assert tr == got.to_bytes(4, "big"), "zlib trailer"
+    n0 = dev_in.numel()
+    assert torch.equal(back[:n0], dev_in), "sharded member: rank 0's slice differs"
+    check = min(total_bytes, 64 * MIB)
+    hostm = member[: min(total, check + (8 << 20))].cpu().numpy().tobytes()
+    zhead = zlib.decompressobj(wbits).decompress(hostm, check)
+    assert zhead == back[:check].cpu().numpy().tobytes(), "sharded member: zlib disagrees on the head"
+    zfull = False
+    if total_bytes <= (2 << 30) and world > 1:
+        full = zlib.decompress(member.cpu().numpy().tobytes(), wbits)
+        assert len(full) == total_bytes and zlib.crc32(full) == (jd.lib.zstrm_crc32update(0xFFFFFFFF, back.data_ptr(), total_bytes) ^ 0xFFFFFFFF)
+        zfull = True
+        del full
+    log(f"sharded stream verified: {world} parts, {total} compressed bytes, decoded {total_bytes} bytes in {time.time() - t0:.1f}s")
+    return {"parts": world, "compressed_bytes": total, "offsets": offs, "decoded_by": ["jdeflate-b200 inflator (whole)",
+            "zlib (whole)" if zfull else "zlib (first %d MiB)" % (check >> 20)], "trailer": trailer, "ok": True}
+
+
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
@@ -227,7 +292,11 @@ def _main(real_stdout):
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mib", type=int, default=1024, help="uncompressed MiB per GPU per step")
     ap.add_argument("--level", type=int, default=6)
-    ap.add_argument("--records", type=int, default=8192, help="distinct zlib JSON records of the inflate leg")
+    ap.add_argument("--records", type=int, default=65536, help="distinct zlib JSON records of the batched inflate leg (C3)")
+    ap.add_argument("--record-count", type=int, default=1 << 20, help="records per step of the batched inflate leg (C3), all ranks together")
+    ap.add_argument("--c4-gib", type=float, default=16.0, help="GiB of LOGS of the sharded zlib level-9 leg (C4), all ranks together")
+    ap.add_argument("--no-c4", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-inflate", action="store_true")
@@ -255,29 +324,51 @@ def _main(real_stdout):
 
     jd = api.load()
     assert jd.lib.jdb200_set_device(local) == 0, jd.lib.jdb200_last_error()
+    from jdeflate_b200 import shard
     corpus = corpus_lib()
-    n = args.mib * MIB
+    chunk_bytes = int(os.environ.get("JDB200_CHUNK_KIB", "512")) << 10
+    # ONE gzip member over the whole job: the slice of this rank (weak scaling: --mib per rank)
+    total_bytes = world * args.mib * MIB
+    sp = shard.plan(total_bytes, world, rank, chunk_bytes)
+    n = sp.end - sp.begin
     cap = n + n // 8 + 65536
+    GZ_HEAD = bytes([0x1F, 0x8B, 8, 0, 0, 0, 0, 0, 0, 0xFF])
 
     # ---- workload: this rank's slice of the mixed corpus, generated into pinned host memory ----
     t0 = time.time()
     host_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-    fill_parallel(corpus, MIXED, host_in.data_ptr(), n, offset=rank * n)
+    fill_parallel(corpus, MIXED, host_in.data_ptr(), n, offset=sp.begin)
     dev_in = host_in.cuda(non_blocking=False)
     dev_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
-    log(f"[rank {rank}] corpus ready in {time.time() - t0:.1f}s")
+    head_len = len(GZ_HEAD) if rank == 0 else 0
+    gz_head = torch.frombuffer(bytearray(GZ_HEAD), dtype=torch.uint8).pin_memory()
+    gz_tail = torch.zeros(8, dtype=torch.uint8).pin_memory()
+    log(f"[rank {rank}] corpus ready in {time.time() - t0:.1f}s (bytes {sp.begin}..{sp.end} of {total_bytes}, last={sp.last})")
 
     d = jd.deflator(args.level)
     state = {}
 
     def step_device():
+        """One pass: gzip header (rank 0), raw DEFLATE of the slice, CRC-32 of the slice, the
+        all_gather that fixes offsets and the member CRC, the trailer (last rank) -- all in HBM."""
+        if head_len:
+            dev_out[:head_len].copy_(gz_head, non_blocking=True)
         d.reset()
         d.setsrc(dev_in.data_ptr(), n)
-        d.settgt(dev_out.data_ptr(), cap)
-        r = d.deflate(api.DEFLT_END)
+        d.settgt(dev_out.data_ptr() + head_len, cap - head_len - 8)
+        r = d.deflate(api.DEFLT_END if sp.last else api.DEFLT_FLUSH)
         assert r == api.OK, (r, d.error, jd.lib.jdb200_last_error())
-        crc = jd.lib.zstrm_crc32update(0xFFFFFFFF, dev_in.data_ptr(), n) ^ 0xFFFFFFFF      # gzip trailer
-        state["produced"], state["crc"] = d.tgtend(), crc
+        crc = jd.lib.zstrm_crc32update(0xFFFFFFFF, dev_in.data_ptr(), n) ^ 0xFFFFFFFF
+        produced = head_len + d.tgtend()
+        member_crc, member_len, offset, total_comp = crc, n, 0, produced
+        if dist is not None:
+            # the one collective of the path, every step
+            offset, offsets, total_comp, member_crc, member_len = shard.exchange(dist, "cuda", produced + (8 if sp.last else 0), crc, n, "crc32")
+        if sp.last:
+            gz_tail.numpy()[:] = np.frombuffer(member_crc.to_bytes(4, "little") + (member_len & 0xFFFFFFFF).to_bytes(4, "little"), np.uint8)
+            dev_out[produced:produced + 8].copy_(gz_tail, non_blocking=True)
+            produced += 8
+        state.update(produced=produced, crc=crc, member_crc=member_crc, offset=offset, total_comp=total_comp)
 
     def barrier():
         torch.cuda.synchronize()
@@ -299,11 +390,6 @@ def _main(real_stdout):
     e0.record()
     for _ in range(args.steps):
         step_device()
-    if dist is not None:
-        # the one collective of the path: per rank {compressed bytes, crc, length} -> offsets + stream CRC
-        mine = torch.tensor([state["produced"], state["crc"], n], dtype=torch.int64, device="cuda")
-        allv = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allv, mine)
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -315,18 +401,25 @@ def _main(real_stdout):
     prof = jd.profile_read()
     jd.profile(False)
     ms_step = ms_total / args.steps
-    value = world * n / (ms_step / 1e3) / 1e9
+    value = total_bytes / (ms_step / 1e3) / 1e9
     produced = state["produced"]
     launches = sum(v[0] for v in prof.values())
 
-    # correctness of what was timed (not in the timed region): zlib decodes it back, CRC matches
-    comp = dev_out[:produced].cpu().numpy().tobytes()
-    check_n = min(n, 64 * MIB)
-    dz = zlib.decompressobj(-15)
-    back = dz.decompress(comp, check_n)
-    assert back == host_in[:check_n].numpy().tobytes(), "decoded bytes differ from the input"
+    # correctness of what was timed (not in the timed region)
     assert state["crc"] == zlib.crc32(host_in.numpy()), "CRC-32 mismatch"
-    del comp, back
+    sharded = None
+    if dist is None:
+        # the gzip member decodes through zlib (first 64 MiB), carries the right trailer, and our
+        # own inflator gives the whole input back
+        comp = dev_out[:produced].cpu().numpy().tobytes()
+        check_n = min(n, 64 * MIB)
+        back = zlib.decompressobj(31).decompress(comp, check_n)
+        assert back == host_in[:check_n].numpy().tobytes(), "decoded bytes differ from the input"
+        assert comp[:10] == GZ_HEAD and comp[-8:-4] == state["crc"].to_bytes(4, "little") and comp[-4:] == (n & 0xFFFFFFFF).to_bytes(4, "little")
+        del comp, back
+    else:
+        sharded = verify_sharded(jd, api, torch, np, dist, rank, world, dev_in, dev_out, produced, state, total_bytes, 31, log)
+    raw_produced = produced - head_len - (8 if sp.last else 0)
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     peak, peak_src = measured_peaks()
@@ -335,7 +428,7 @@ def _main(real_stdout):
     deflate_kernels = {k: v for k, v in prof.items() if not k.startswith("ck_")}
     # one launch of a deflate-pipeline kernel covers one batch: algorithmic bytes = N (read) + C (written)
     nbatches = max(1, sum(v[0] for k, v in prof.items() if k.startswith("lz_kernel")) or args.steps)
-    alg_bytes_per_launch = (n + produced) * args.steps / nbatches
+    alg_bytes_per_launch = (n + raw_produced) * args.steps / nbatches
     achieved = alg_bytes_per_launch / (dom_ms / max(dom_launches, 1) / 1e3) / 1e9 if dom_ms else 0.0
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
@@ -441,7 +534,22 @@ def _main(real_stdout):
     # ---- inflate leg: batched zlib JSON records (BASELINE configs[2], scaled) ----------------------------
     inflate = None
     if not args.no_inflate:
-        inflate = bench_inflate(jd, corpus, args, torch, np, barrier, peak)
+        inflate = bench_inflate(jd, corpus, args, torch, np, barrier, peak, rank, world, dist)
+
+    # ---- the other BASELINE configs at their stated sizes ---------------------------------------------------
+    c5 = None
+    if not args.no_c5:
+        try:
+            c5 = bench_c5(jd, args, torch, np, barrier, host_in, n, dist, world, e2e)
+        except Exception as ex:                                       # reported, never required
+            if dist is not None:
+                raise
+            c5 = {"note": f"failed: {ex!r}"}
+    c4 = None
+    if not args.no_c4:
+        del dev_out
+        torch.cuda.empty_cache()
+        c4 = bench_c4(jd, corpus, args, torch, np, barrier, rank, world, dist, chunk_bytes)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
@@ -467,10 +575,11 @@ def _main(real_stdout):
             "metric": "deflate_level%d_GBps_uncompressed" % args.level, "value": round(value, 3), "unit": "GB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args, {"chunk_kib": int(os.environ.get("JDB200_CHUNK_KIB", "512")),
-                                             "collective": "all_gather of 24 B per rank" if world > 1 else "none"}),
-            "ratio": round(n / produced, 4), "compressed_bytes_per_gpu": produced,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "inflate": inflate, "checksum": checksum,
+            "config": workload_config(args, {"chunk_kib": chunk_bytes >> 10,
+                                             "collective": "all_gather of 24 B per rank, every step" if world > 1 else "none",
+                                             "sharding": "one gzip member over %d ranks: DEFLT_FLUSH on all but the last" % world if world > 1 else "none"}),
+            "ratio": round(n / raw_produced, 4), "compressed_bytes_per_gpu": produced, "sharded": sharded,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "inflate": inflate, "c4": c4, "c5": c5, "checksum": checksum,
             "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), file=real_stdout, flush=True)
@@ -480,18 +589,195 @@ def _main(real_stdout):
     return 0
 
 
-def bench_inflate(jd, corpus, args, torch, np, barrier, peak):
-    """Batched inflate of independent zlib JSON records (4-64 KiB, zlib level 6 = third-party
-    streams), one warp per record, device-resident buffers."""
-    from jdeflate_b200 import api
-    nd = args.records
+def bench_c4(jd, corpus, args, torch, np, barrier, rank, world, dist, chunk_bytes):
+    """BASELINE configs[3]: zlib level 9 of 16 GiB of synthetic logs as ONE zlib stream, strong-scaled
+    over the ranks (16/N GiB each): slices from shard.plan() at the codec's chunk size, DEFLT_FLUSH
+    on every rank but the last owner, the all_gather of {compressed bytes, Adler-32, length} inside
+    every timed step; afterwards rank 0 gathers the parts once and decodes header + parts + trailer."""
+    from jdeflate_b200 import api, shard
+    LOGS = 1
+    total_bytes = int(args.c4_gib * (1 << 30)) // (world * chunk_bytes) * (world * chunk_bytes)
+    sp = shard.plan(total_bytes, world, rank, chunk_bytes)
+    n = sp.end - sp.begin
     t0 = time.time()
-    recs = [corpus.json_record(i) for i in range(nd)]
-    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
-        comp = list(ex.map(lambda r: zlib.compress(r, 6), recs))
-    tile = max(1, (1 << 30) // max(1, sum(map(len, recs))))          # ~1 GiB of output per step
-    count = nd * tile
-    perm = np.random.RandomState(1).permutation(count) % nd
+    host = np.empty(n, np.uint8)
+    fill_parallel(corpus, LOGS, host.ctypes.data, n, offset=sp.begin)
+    dev_in = torch.empty(n, dtype=torch.uint8, device="cuda")
+    piece = 256 * MIB
+    for off in range(0, n, piece):
+        dev_in[off:off + piece].copy_(torch.from_numpy(host[off:off + piece]))
+    del host
+    cap = n // 2 + n // 8 + (64 << 20)            # logs compress > 4:1; the encoder reports TGTEXHSTD otherwise
+    dev_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    ZHEAD = bytes([0x78, 0xDA])
+    head_len = 2 if rank == 0 else 0
+    zhead = torch.frombuffer(bytearray(ZHEAD), dtype=torch.uint8).pin_memory()
+    ztail = torch.zeros(4, dtype=torch.uint8).pin_memory()
+    log(f"[rank {rank}] C4: {n / (1 << 30):.2f} GiB of logs ready in {time.time() - t0:.1f}s")
+    d = jd.deflator(9)
+    state = {}
+
+    def step():
+        if head_len:
+            dev_out[:head_len].copy_(zhead, non_blocking=True)
+        d.reset()
+        d.setsrc(dev_in.data_ptr(), n)
+        d.settgt(dev_out.data_ptr() + head_len, cap - head_len - 4)
+        r = d.deflate(api.DEFLT_END if sp.last else api.DEFLT_FLUSH)
+        assert r == api.OK, (r, d.error, jd.lib.jdb200_last_error())
+        adler = jd.lib.zstrm_adler32update(1, dev_in.data_ptr(), n)
+        produced = head_len + d.tgtend()
+        member, length, offset, total_comp = adler, n, 0, produced
+        if dist is not None:
+            offset, offsets, total_comp, member, length = shard.exchange(dist, "cuda", produced + (4 if sp.last else 0), adler, n, "adler32")
+        if sp.last:
+            ztail.numpy()[:] = np.frombuffer(member.to_bytes(4, "big"), np.uint8)
+            dev_out[produced:produced + 4].copy_(ztail, non_blocking=True)
+            produced += 4
+        state.update(produced=produced, member_crc=member, offset=offset, total_comp=total_comp)
+
+    step()
+    jd.profile(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    steps = 2
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    prof = jd.profile_read()
+    jd.profile(False)
+    ver = verify_sharded(jd, api, torch, np, dist, rank, world, dev_in, dev_out, state["produced"], state, total_bytes, 15, log,
+                         trailer="adler32")
+    d.close()
+    if rank != 0:
+        return None
+    return {"value": round(total_bytes / (ms / 1e3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(ms, 2), "steps": steps,
+            "scaling": "strong", "workload": "zlib level 9 of %.2f GiB of synthetic logs as one stream over %d rank(s) "
+            "[BASELINE configs[3]]" % (total_bytes / (1 << 30), world), "bytes": total_bytes, "bytes_per_gpu": n,
+            "ratio": round(total_bytes / ver["compressed_bytes"], 4), "sharded": ver,
+            "kernel_ms_per_step": {k: round(v[1] / steps, 2) for k, v in sorted(prof.items()) if v[1] > 0.5 * steps}}
+
+
+def bench_c5(jd, args, torch, np, barrier, host_in, n, dist, world, e2e_l6):
+    """BASELINE configs[4]: the zstrm gzip streaming pipeline with 8 MiB callbacks and HOST buffers,
+    compress and decompress, level 1 and level 6 (the reference's zstrm_deflate / zstrm_inflate with
+    callback I/O, src/zstrm.c:792-958, 1112-1313).  Every byte crosses PCIe inside the timed region.
+    GB/s of uncompressed bytes; at N > 1 every rank runs its own pipeline (aggregate, max time)."""
+    import ctypes as C
+    from jdeflate_b200 import api
+    piece = 8 * MIB
+    cap = n + n // 8 + 65536
+    host_gz = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    host_back = torch.empty(piece, dtype=torch.uint8, pin_memory=True)
+    gz_base, in_base = host_gz.data_ptr(), host_in.data_ptr()
+    want_crc = zlib.crc32(host_in.numpy())
+    out = {}
+
+    def agg(secs):
+        if dist is not None:
+            t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t.item())
+        return round(world * n / secs / 1e9, 3)
+
+    for level in (1, 6):
+        pos = {"p": 0}
+
+        def sink(buf, size, user):
+            C.memmove(gz_base + pos["p"], buf, size)
+            pos["p"] += size
+            return size
+        ocb = api.OFN(sink)
+        z = jd.lib.zstrm_create(api.ZSTRM_DEFLATE | api.ZSTRM_GZIP, level, None)
+        assert z
+
+        def compress():
+            jd.lib.zstrm_reset(z)
+            pos["p"] = 0
+            jd.lib.zstrm_settargetfn(z, ocb, None)
+            for off in range(0, n, piece):
+                k = min(piece, n - off)
+                assert jd.lib.zstrm_deflate(z, in_base + off, k) == k, z.contents.error
+            jd.lib.zstrm_flush(z, 1)
+            assert z.contents.error == 0
+
+        compress()
+        barrier()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            compress()
+        barrier()
+        csecs = (time.perf_counter() - t0) / reps
+        gz_len = pos["p"]
+        jd.lib.zstrm_destroy(z)
+
+        rd = {"p": 0}
+
+        def source(buf, size, user):
+            k = min(size, piece, gz_len - rd["p"])
+            C.memmove(buf, gz_base + rd["p"], k)
+            rd["p"] += k
+            return k
+        icb = api.IFN(source)
+        zi = jd.lib.zstrm_create(api.ZSTRM_INFLATE | api.ZSTRM_GZIP, 0, None)
+        assert zi
+
+        def decompress(check):
+            jd.lib.zstrm_reset(zi)
+            rd["p"] = 0
+            jd.lib.zstrm_setsourcefn(zi, icb, None)
+            total, crc = 0, 0
+            while True:
+                got = jd.lib.zstrm_inflate(zi, host_back.data_ptr(), piece)
+                if got <= 0:
+                    break
+                if check:
+                    crc = zlib.crc32(host_back.numpy()[:got], crc)
+                total += got
+            assert zi.contents.error == 0 and total == n, (zi.contents.error, total)
+            if check:
+                assert crc == want_crc, "C5: decompressed bytes differ"
+
+        decompress(True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            decompress(False)
+        barrier()
+        dsecs = (time.perf_counter() - t0) / reps
+        jd.lib.zstrm_destroy(zi)
+        out["level%d" % level] = {"deflate": agg(csecs), "inflate": agg(dsecs), "unit": "GB/s", "ratio": round(n / gz_len, 4),
+                                  "h2d_d2h_bytes_per_step": {"deflate": [n, gz_len], "inflate": [gz_len, n]}}
+    out["workload"] = ("zstrm gzip streaming compress + decompress of %d MiB mixed corpus per GPU, host (pinned) buffers, 8 MiB "
+                       "pieces through the target / source callbacks [BASELINE configs[4]]" % (n // MIB))
+    if e2e_l6:
+        out["level6"]["deflate_headline_e2e"] = e2e_l6["value"]
+    return out
+
+
+def bench_inflate(jd, corpus, args, torch, np, barrier, peak, rank=0, world=1, dist=None):
+    """BASELINE configs[2] at its stated size: batched inflate of 1 Mi independent zlib JSON records
+    (4-64 KiB, zlib level 6 = third-party streams, 65 536 distinct ones in a random permutation: the
+    compressed working set is far larger than the L2), one warp per record, device-resident
+    buffers.  At N > 1 the records are dealt out to the ranks."""
+    from jdeflate_b200 import api
+    nd = max(1, args.records // world)
+    count = max(nd, args.record_count // world)
+    t0 = time.time()
+    workers = min(32, os.cpu_count() or 1)
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        recs = list(ex.map(lambda i: corpus.json_record(i + rank * nd), range(nd), chunksize=64))
+        comp = list(ex.map(lambda r: zlib.compress(r, 6), recs, chunksize=64))
+    tile = count // nd
+    perm = np.random.RandomState(1 + rank).permutation(count) % nd
     clen = np.array([len(x) for x in comp], np.uint64)
     rlen = np.array([len(x) for x in recs], np.uint64)
     src_off = np.zeros(nd + 1, np.uint64)
@@ -519,20 +805,28 @@ def bench_inflate(jd, corpus, args, torch, np, barrier, peak):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    steps = max(3, args.steps)
+    steps = min(max(3, args.steps), 5)
     for _ in range(steps):
         step()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / steps
+    job_out, job_in, job_count = total_out, total_in, count
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        t = torch.tensor([total_out, total_in, count], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        job_out, job_in, job_count = (int(x) for x in t.tolist())
     prof = jd.profile_read()
     jd.profile(False)
     res = dres.cpu().numpy().view(np.uint32).reshape(count, 8)
     assert int((res[:, 0] != 0).sum()) == 0 and int((res[:, 2] != 0).sum()) == 0, "inflate batch reported errors"
-    host = out.cpu().numpy()
-    for k in range(0, count, max(1, count // 64)):
+    # every record's Adler-32 trailer was checked by the kernel (zerror); bytes of a sample, too
+    for k in range(0, count, max(1, count // 256)):
         o, ln = int(items[k, 1]), int(items[k, 3])
-        assert host[o:o + ln].tobytes() == recs[perm[k]], "inflate output mismatch"
+        assert out[o:o + ln].cpu().numpy().tobytes() == recs[perm[k]], "inflate output mismatch"
     # the compress-side mirror: the same records, each into its own zlib stream
     batch = None
     try:
@@ -558,23 +852,22 @@ def bench_inflate(jd, corpus, args, torch, np, barrier, peak):
         barrier()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
-        for _ in range(3):
+        for _ in range(2):
             cstep()
         c1.record()
         barrier()
-        cms = c0.elapsed_time(c1) / 3
+        cms = c0.elapsed_time(c1) / 2
         rr = r2.cpu().numpy()
         assert not (rr.view(np.uint32).reshape(count, 8)[:, 0]).any(), "deflate batch reported errors"
         used = rr.view(np.uint64).reshape(count, 4)[:, 3]
-        hostc = cout.cpu().numpy()
-        for k in range(0, count, max(1, count // 64)):
+        for k in range(0, count, max(1, count // 256)):
             o, n = int(it2[k, 1]), int(used[k])
-            assert zlib.decompress(hostc[o:o + n].tobytes()) == recs[perm[k]], "deflate batch stream mismatch"
+            assert zlib.decompress(cout[o:o + n].cpu().numpy().tobytes()) == recs[perm[k]], "deflate batch stream mismatch"
         batch = {"value": round(total_out / (cms / 1e3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(cms, 3),
                  "records_per_s": round(count / (cms / 1e3), 1), "ratio": round(total_out / float(used.sum()), 4),
                  "zlib_ratio": round(total_out / float(total_in), 4),
                  "api": f"jdb200_deflate_batch(JDB200_ZLIB, level {args.level}) on the same {count} records, device buffers"}
-        del rsrc, cout, d2, r2, hostc
+        del rsrc, cout, d2, r2
     except Exception as ex:                                           # reported, never required
         batch = {"value": None, "note": f"failed: {ex}"}
     # one large stream of OURS through the plain inflator (chunk-parallel decode)
@@ -611,12 +904,44 @@ def bench_inflate(jd, corpus, args, torch, np, barrier, peak):
         del draw, dcomp, dback
     except Exception as ex:                                           # reported, never required
         own = {"value": None, "note": f"failed: {ex}"}
+    # ONE third-party stream (zlib level 6, no sync markers) through the plain inflator: nothing to
+    # parallelise over, the sequential decoder (the reference's decodefast on one core: 0.25-0.33 GB/s)
+    single = None
+    try:
+        nsingle = 64 * MIB
+        raw1 = np.empty(nsingle, np.uint8)
+        fill_parallel(corpus, MIXED, raw1.ctypes.data, nsingle, offset=0)
+        z1 = zlib.compress(raw1.tobytes(), 6)[2:-4]
+        dz1 = torch.from_numpy(np.frombuffer(z1, np.uint8).copy()).cuda()
+        dback1 = torch.empty(nsingle, dtype=torch.uint8, device="cuda")
+        best = None
+        for _ in range(2):
+            si = jd.inflator()
+            si.setsrc(dz1.data_ptr(), len(z1))
+            si.settgt(dback1.data_ptr(), nsingle)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rr = si.inflate(1)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            assert rr == api.OK and si.tgtend() == nsingle and si.srcend() == len(z1)
+            si.close()
+            best = dt if best is None else min(best, dt)
+        assert dback1.cpu().numpy().tobytes() == raw1.tobytes()
+        single = {"value": round(nsingle / best / 1e9, 4), "unit": "GB/s", "bytes_out": nsingle,
+                  "api": "inflator_inflate(final) on one raw zlib level-6 stream of the mixed corpus (device buffers)"}
+        del dz1, dback1
+    except Exception as ex:                                           # reported, never required
+        single = {"value": None, "note": f"failed: {ex}"}
     kms = prof.get("inflate_batch_kernel", (steps, ms * steps))
     kavg = kms[1] / max(kms[0], 1)
     ach = (total_in + total_out) / (kavg / 1e3) / 1e9
-    return {"value": round(total_out / (ms / 1e3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(ms, 3),
-            "workload": f"batched inflate of {count} zlib level-6 JSON records (4-64 KiB, {nd} distinct) [BASELINE configs[2] scaled]",
-            "records": count, "bytes_out": total_out, "bytes_in": total_in, "own_stream": own, "deflate_batch": batch,
+    return {"value": round(job_out / (ms / 1e3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(ms, 3),
+            "workload": f"batched inflate of {job_count} zlib level-6 JSON records (4-64 KiB, {nd * world} distinct, random permutation"
+                        f"{', dealt out to %d ranks' % world if world > 1 else ''}) [BASELINE configs[2]]",
+            "records": job_count, "distinct": nd * world, "bytes_out": job_out, "bytes_in": job_in,
+            "distinct_compressed_bytes": int(clen.sum()) * world, "records_per_s": round(job_count / (ms / 1e3), 1),
+            "own_stream": own, "single_third_party": single, "deflate_batch": batch,
             "roofline": {"bound": "hbm", "kernel": "inflate_batch_kernel", "achieved": round(ach, 2), "peak": peak,
                          "unit": "GB/s", "frac": round(ach / peak, 5), "avg_launch_ms": round(kavg, 4)}}
 

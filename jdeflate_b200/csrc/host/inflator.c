@@ -78,6 +78,9 @@ struct TINFLTPrvt {
 	uint32 par_fin;         /* the last fragment ends the stream (BFINAL marker) */
 	uint32 par_starved;     /* the step stopped because the input ended inside a chunk */
 	size_t par_seen;        /* queued bytes that step has seen */
+	size_t readahead;       /* zstrm: the caller signals the end of the input with `final`, so a chain under way may
+	                         * wait for this much input before the next step (a step takes as long as its slowest chunk) */
+	size_t par_want;        /* queued bytes the next step of a chain waits for */
 	jdb_dbuf   outbuf;
 
 	jdb_inflate_state* dstate;
@@ -175,6 +178,7 @@ inflator_reset(TInflator* state)
 	PRVT->par_total = 0;
 	PRVT->par_nfrag = PRVT->par_cur = PRVT->par_off = PRVT->par_fin = PRVT->par_starved = 0;
 	PRVT->par_seen = 0;
+	PRVT->par_want = PAR_MIN_BYTES;
 	if (PRVT->par_stride == 0) {
 		PRVT->par_stride = PAR_STRIDE;
 	}
@@ -255,6 +259,12 @@ void
 jdb_inflator_set_checks(TInflator* state, int which)
 {
 	PRVT->checks = which;
+}
+
+void
+jdb_inflator_set_readahead(TInflator* state, size_t bytes)
+{
+	PRVT->readahead = bytes;
 }
 
 int
@@ -576,6 +586,11 @@ parallel_step(struct TINFLTPrvt* state)
 	PRVT->inqoff += (size_t) used;
 	PRVT->inqlen -= (size_t) used;
 	PRVT->par_seen = PRVT->inqlen;
+	/* the next step of this chain: four times the input of this one, up to the read-ahead */
+	PRVT->par_want = (size_t) used * 4 > PAR_MIN_BYTES ? (size_t) used * 4 : PAR_MIN_BYTES;
+	if (PRVT->readahead && PRVT->par_want > PRVT->readahead) {
+		PRVT->par_want = PRVT->readahead;
+	}
 	PRVT->par_nfrag = nfrag;
 	PRVT->par_fin = (uint32) fin;
 	return 1;
@@ -704,8 +719,17 @@ inflator_inflate(TInflator* state, uint32 final)
 		/* a stream cut into chunks by sync markers (ours) is decoded chunk-parallel
 		 * while the decoder sits at a block boundary */
 		if (PRVT->par_ok) {
-			int step = PRVT->inqlen >= PAR_MIN_BYTES ||
+			const int chain = PRVT->readahead && PRVT->par_total != 0 && PRVT->par_starved;
+			int step = PRVT->inqlen >= (chain ? PRVT->par_want : PAR_MIN_BYTES) ||
 			           (PBLC->finalinput && absorbed_all && PRVT->inqlen >= ((size_t) 256 << 10));
+			if (!step && chain && !PBLC->finalinput) {
+				/* zstrm feeds a chain of chunks and promises `final` at the end of its input:
+				 * gather more of it, a step over many chunks takes no longer than one over few */
+				if (absorbed_all) {
+					return (eINFLTResult) (PBLC->status = INFLT_SRCEXHSTD);
+				}
+				continue;
+			}
 			if (!step && PRVT->par_starved) {
 				/* a streaming caller with small windows: the last step stopped because the
 				 * queue ended inside a chunk (or right after one).  Nothing new: ask for

@@ -13,6 +13,7 @@ int  jdb_deflator_get_checks(TDeflator* d, uint32* crc, uint32* adler);
 
 /* same for the bytes an inflator produces */
 void jdb_inflator_set_checks(TInflator* s, int which);
+void jdb_inflator_set_readahead(TInflator* s, size_t bytes);
 int  jdb_inflator_get_checks(TInflator* s, uint32* crc, uint32* adler);
 
 #endif

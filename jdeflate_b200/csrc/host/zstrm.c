@@ -22,6 +22,7 @@
 #include "jdb_internal.h"
 
 #define ZS_IOBYTES   ((size_t) 8 << 20)
+#define ZS_READAHEAD ((size_t) 256 << 20)
 #define ZS_DIRECT    ((size_t) 256 << 10)   /* reads at least this big decode in place */
 
 #define ZSTRM_MODEMASK 0x000f0000u
@@ -46,6 +47,7 @@ struct TZStrmPrvt {
 	struct TInflator* infltr;
 	uint32 result;          /* last inflator / deflator status */
 	uint32 srcset;          /* the inflator holds an unfinished source window */
+	uint32 srceof;          /* the source has nothing more to give: the inflator is told (final) */
 
 	/* inflate: compressed bytes not yet handed to the inflator */
 	const uint8* sbgn;
@@ -195,11 +197,15 @@ zstrm_reset(const TZStrm* state)
 
 	zstrm->result = 0;
 	zstrm->srcset = 0;
+	zstrm->srceof = 0;
 	if (zstrm->public.smode == ZSTRM_INFLATE) {
 		zstrm->doadler = (zstrm->public.flags & ZSTRM_DOADLER) != 0;
 		zstrm->docrc   = (zstrm->public.flags & ZSTRM_DOCRC)   != 0;
 		inflator_reset(zstrm->infltr);
 		jdb_inflator_set_checks(zstrm->infltr, 0);
+		/* the end of the input is reported to the inflator (see inflate()), so a stream of
+		 * independent chunks may gather this much input per chunk-parallel step */
+		jdb_inflator_set_readahead(zstrm->infltr, ZS_READAHEAD);
 	}
 	else {
 		deflator_reset(zstrm->defltr);
@@ -557,25 +563,41 @@ inflate(struct TZStrmPrvt* zstrm, uint8* buffer, uintxx total)
 			break;
 		}
 		if (zstrm->result == INFLT_SRCEXHSTD || zstrm->srcset == 0) {
-			if (zstrm->sbgn == zstrm->send) {
+			if (zstrm->sbgn == zstrm->send && !zstrm->srceof) {
 				if (zstrm->iofn) {
 					intxx r = zstrm->iofn(zstrm->ibuf, ZS_IOBYTES, zstrm->user);
-					if (r <= 0 || (uintxx) r > ZS_IOBYTES) {
-						fail(zstrm, r == 0 ? ZSTRM_EBADDATA : ZSTRM_EIOERROR);
+					if (r < 0 || (uintxx) r > ZS_IOBYTES) {
+						fail(zstrm, ZSTRM_EIOERROR);
 						break;
+					}
+					if (r == 0) {
+						zstrm->srceof = 1;
 					}
 					zstrm->sbgn = zstrm->ibuf;
 					zstrm->send = zstrm->ibuf + r;
 				}
 				else {
-					fail(zstrm, ZSTRM_ESRCEXHSTD);
+					zstrm->srceof = 1;
+				}
+				if (zstrm->srceof && zstrm->result != INFLT_SRCEXHSTD) {
+					/* nothing was ever fed */
+					fail(zstrm, zstrm->iofn ? ZSTRM_EBADDATA : ZSTRM_ESRCEXHSTD);
 					break;
 				}
 			}
-			inflator_setsrc(infltr, zstrm->sbgn, (uintxx) (zstrm->send - zstrm->sbgn));
+			else if (zstrm->sbgn == zstrm->send) {
+				/* the end of the input was reported to the inflator and it still wants more */
+				fail(zstrm, zstrm->iofn ? ZSTRM_EBADDATA : ZSTRM_ESRCEXHSTD);
+				break;
+			}
+			if (zstrm->send != zstrm->sbgn) {
+				inflator_setsrc(infltr, zstrm->sbgn, (uintxx) (zstrm->send - zstrm->sbgn));
+				zstrm->wbase = zstrm->sbgn;
+				zstrm->wused = 0;
+			}
+			/* else: the end of the input; the inflator keeps its (used up) window and is told
+			 * `final` below -- it may have been gathering input for a chunk-parallel step */
 			zstrm->srcset = 1;
-			zstrm->wbase = zstrm->sbgn;
-			zstrm->wused = 0;
 		}
 
 		/* 3. big reads decode straight into the caller's memory, small ones
@@ -590,8 +612,14 @@ inflate(struct TZStrmPrvt* zstrm, uint8* buffer, uintxx total)
 			cap = ZS_IOBYTES;
 		}
 		inflator_settgt(infltr, tgt, cap);
-		zstrm->result = inflator_inflate(infltr, 0);
+		zstrm->result = inflator_inflate(infltr, zstrm->srceof ? 1 : 0);
 		n = inflator_tgtend(infltr);
+		if (zstrm->result == INFLT_ERROR && zstrm->srceof && infltr->error == INFLT_EINPUTEND && n == 0) {
+			/* the stream is longer than the input (the reference: the callback has nothing
+			 * more to give, src/zstrm.c:842-858) */
+			fail(zstrm, zstrm->iofn ? ZSTRM_EBADDATA : ZSTRM_ESRCEXHSTD);
+			break;
+		}
 
 		/* the inflator holds [wbase, send); srcend() is how much of it is gone
 		 * for good -- it can shrink at the end of the stream, when the bytes
