@@ -39,7 +39,7 @@
 #endif
 #define INF_THREADS      (INF_WARPS * 32)
 #ifndef LIT_ROOT
-#define LIT_ROOT         10
+#define LIT_ROOT         JDB_INF_LIT_ROOT
 #endif
 #define DIST_ROOT        8
 #ifndef LIT_TABLE
@@ -55,6 +55,30 @@
 #endif
 #define RING_KEEP        (RING - MAXBATCH - 258u)
 #define INW              256u      /* words of staged input per warp (1 KiB) */
+
+/* lane-parallel symbol decode (see par_round): every lane decodes its own PAR_S-bit
+ * subsequence of the input window into PQ_K token slots */
+#ifndef PQ_K
+#define PQ_K             32u
+#endif
+#ifndef PAR_S0
+#define PAR_S0           192u      /* subsequence length in bits: first guess, then adaptive */
+#endif
+#define PAR_SMIN         64u
+#define PAR_SMAX         192u      /* 32 * PAR_SMAX + 64 bits must fit the input ring with one fill granule to spare */
+#ifndef PAR_MAXPASS
+#define PAR_MAXPASS      8
+#endif
+#ifdef LANE_NOINLINE
+#define LANE_INLINE __noinline__
+#else
+#define LANE_INLINE __forceinline__
+#endif
+#define PF_OK            0u        /* ran to its boundary */
+#define PF_EOB           1u        /* decoded the end-of-block symbol */
+#define PF_ANOM          2u        /* met something the step-by-step decoder has to judge */
+#define PF_FULL          3u        /* token slots used up before the boundary */
+#define PF_STOP          4u        /* reached the end of the safely decodable input */
 
 /* table entry: value<<16 | type<<8 | extra<<4 | nbits   (nbits==0: invalid) */
 #define T_LIT   0u
@@ -108,9 +132,12 @@ struct BuildMem {
 struct WarpMem {
 	uint32_t lit[LIT_TABLE];
 	uint32_t dist[DIST_TABLE];
-	uint32_t queue[QUEUE];
 	uint32_t inbuf[INW];           /* ring of staged input words (symbol loop) */
-	BuildMem bm;
+	uint32_t pend[2];              /* a match cut by the end of the target: rest length, distance */
+	union {
+		BuildMem bm;                    /* block header */
+		uint32_t cq[PQ_K * 32u];        /* symbol loop: token slot i of lane l at cq[i * 32 + l], then compacted */
+	};
 	uint8_t  ring[RING];
 };
 
@@ -121,7 +148,7 @@ enum { KIND_LIT = 0, KIND_DIST = 1, KIND_PRE = 2 };
  * Returns 0, or 1 when the length set is not acceptable (rules of
  * src/inflator.c:428-474).  All lanes call it; all lanes get the result.
  */
-static __device__ int
+static __device__ __noinline__ int
 build_table(BuildMem* m, uint32_t* table, int n, int kind, int lenoff)
 {
 	const unsigned lane = jdb_lane();
@@ -432,131 +459,222 @@ struct Stream {
 	uint64_t consumed;          /* source bytes used by this call */
 	uint64_t hist_avail;        /* bytes available before dst[0] (history / dictionary) */
 	uint64_t total_before;      /* absolute output position of dst[0] (ring index base) */
-	uint8_t* ring;              /* shared-memory copy of the newest RING output bytes */
+	uint8_t* ring;              /* the newest output bytes, indexed by the low bits of their target address */
 	int64_t  ring_lo;           /* positions >= ring_lo are served from the ring */
+	uint32_t rbase;             /* low bits of dst */
+	uint64_t flushed;           /* bytes [0, flushed) have reached the target */
 	uint32_t status, error;
 };
 
-/* byte at output position `pos` relative to this call's dst: the newest bytes
- * come from the shared-memory ring, older ones from L2, and negative positions
- * from the history ring of earlier calls */
+/*
+ * Output path.  Decoded bytes go to a per-warp ring in shared memory first and from
+ * there to the target in aligned 32-bit words (flush_ring): the symbol loop produces bytes
+ * one or a few at a time per lane, which as global stores are one memory instruction per
+ * byte; the ring takes them at shared-memory cost, serves most match sources (the newest
+ * bytes) and leaves the target with coalesced word stores.  The ring is indexed by the low
+ * bits of the target ADDRESS, so its words line up with the target's words whatever the
+ * alignment of dst.  Positions are relative to this call's dst; negative ones are the
+ * history of earlier calls.
+ */
+static __device__ __forceinline__ uint32_t
+ring_index(const Stream& s, uint32_t pos)
+{
+	return (s.rbase + pos) & (RING - 1u);
+}
+
+/* byte at output position `pos`: the ring has the newest bytes, L2 the older ones (they were
+ * flushed by other lanes of this warp: ld.global.cg), earlier calls' bytes sit in the history ring */
 static __device__ __forceinline__ uint8_t
 out_byte(const Stream& s, int64_t pos)
 {
-	if (pos >= s.ring_lo) return s.ring[(uint32_t) pos & (RING - 1)];
+	if (pos >= s.ring_lo) return s.ring[ring_index(s, (uint32_t) pos)];
 	if (pos >= 0) return __ldcg(s.dst + pos);
 	uint64_t abs = s.total_before + (uint64_t) pos;
 	return __ldcg(s.st->history + (abs & (JDB_INFLATE_HISTORY - 1)));
 }
 
+/* all lanes: bytes [s.flushed, upto) of the ring -> target; without `all` only up to the last
+ * word boundary (the rest follows with the next flush) */
 static __device__ __forceinline__ void
-put_byte(const Stream& s, uint64_t pos, uint8_t v)
+flush_ring(Stream& s, uint64_t upto, bool all)
 {
-	s.dst[pos] = v;
-	if (s.ring) s.ring[(uint32_t) pos & (RING - 1)] = v;
-}
-
-/* warp-cooperative copy of `len` bytes with source `dist` back from `pos` */
-static __device__ __forceinline__ void
-copy_match(const Stream& s, uint64_t pos, uint32_t len, uint32_t dist)
-{
-	/* every source byte lies before `pos` (k < dist), so all loads can be
-	 * issued before the first store */
 	const unsigned lane = jdb_lane();
-	uint8_t tmp[9];                      /* 258 bytes / 32 lanes */
-#pragma unroll
-	for (int i = 0; i < 9; i++) {
-		uint32_t j = lane + 32u * i;
-		if (j < len) {
-			uint32_t k = dist >= len ? j : j % dist;
-			tmp[i] = out_byte(s, (int64_t) (pos - dist) + k);
-		}
-	}
-#pragma unroll
-	for (int i = 0; i < 9; i++) {
-		uint32_t j = lane + 32u * i;
-		if (j < len) put_byte(s, pos + j, tmp[i]);
-	}
+	uint8_t* const a = s.dst + s.flushed;
+	uint8_t* b = s.dst + upto;
+	if (!all) b = (uint8_t*) ((uintptr_t) b & ~(uintptr_t) 3);
+	if (b <= a) return;
+	uint8_t* w0 = (uint8_t*) (((uintptr_t) a + 3) & ~(uintptr_t) 3);
+	if (w0 > b) w0 = b;
+	uint8_t* const w1 = w0 + ((size_t) (b - w0) & ~(size_t) 3);
+	if (a + lane < w0) a[lane] = s.ring[(uint32_t) (uintptr_t) (a + lane) & (RING - 1u)];
+	for (uint8_t* g = w0 + 4u * lane; g < w1; g += 128)
+		*(uint32_t*) g = *(const uint32_t*) (s.ring + ((uint32_t) (uintptr_t) g & (RING - 1u)));
+	if (w1 + lane < b) w1[lane] = s.ring[(uint32_t) (uintptr_t) (w1 + lane) & (RING - 1u)];
+	s.flushed = (uint64_t) (b - s.dst);
+	__syncwarp();
 }
 
 /*
- * All lanes: turn `nq` queued symbols (literal: byte value; match: len << 16 |
- * dist) of stream `s` into output bytes starting at s.out.  A warp prefix sum
- * gives every symbol its offset; literals and short far matches are written by
- * their own lane, long matches and matches that read bytes produced by the
- * same queue are copied cooperatively, in order.  A match cut by the end of
- * the target is reported through pend_len / pend_dist.
+ * All lanes: turn up to `nq` (<= 32) queued symbols (literal: byte value; match: len << 16 |
+ * dist) of stream `s` into output bytes starting at s.out; returns how many it took -- a
+ * group stops growing once it holds MAXBATCH bytes (the ring holds one group plus at least
+ * RING_KEEP older bytes).  A warp prefix sum gives every symbol its offset; literals and
+ * short matches whose source is older than the group are written by their own lane, long
+ * matches and matches that read bytes produced by the same group are copied by all lanes,
+ * in order.  A match cut by the end of the target is reported through pend_len / pend_dist.
  */
-static __device__ __forceinline__ void
-emit_queue(Stream& s, BuildMem* bm, const uint32_t* queue, uint32_t nq, uint32_t& pend_len, uint32_t& pend_dist)
+static __device__ __forceinline__ uint32_t
+emit_queue(Stream& s, uint32_t* pend, const uint32_t* queue, uint32_t nq, uint32_t& pend_len, uint32_t& pend_dist)
 {
 	const unsigned lane = jdb_lane();
 	uint32_t q = lane < nq ? queue[lane] : 0;
 	uint32_t len = lane < nq ? ((q >> 16) ? (q >> 16) : 1u) : 0u;
-	const bool is_match = lane < nq && (q >> 16) != 0;
-	uint32_t dist = q & 0xffffu;
 	uint32_t incl = len;
 	for (int o = 1; o < 32; o <<= 1) {
 		uint32_t t = __shfl_up_sync(JDB_FULL_MASK, incl, o);
 		if ((int) lane >= o) incl += t;
 	}
+	/* symbols that would start at or beyond MAXBATCH bytes wait for the next group */
+	{
+		const unsigned over = __ballot_sync(JDB_FULL_MASK, lane < nq && incl - len >= MAXBATCH);
+		if (over) {
+			nq = (uint32_t) __ffs(over) - 1u;
+			if (lane >= nq) { q = 0; len = 0; }
+		}
+	}
+	const bool is_match = lane < nq && (q >> 16) != 0;
+	const uint32_t dist = q & 0xffffu;
 	const uint64_t base = s.out;
-	if (s.ring) {
-		s.ring_lo = (int64_t) base - (int64_t) RING_KEEP;
-		if (s.ring_lo < 0) s.ring_lo = 0;
-	} else {
-		s.ring_lo = 0x7fffffffffffffffll;     /* no shared-memory mirror: re-read from L2 */
-	}
-	const uint64_t pos = base + incl - len;
-	const uint32_t total = __shfl_sync(JDB_FULL_MASK, incl, 31);
+	const uint32_t total = __shfl_sync(JDB_FULL_MASK, incl, (int) nq - 1);
+	const uint32_t off = incl - len;                     /* of this symbol, from `base` */
 	/* clip the last symbol to the target capacity */
+	const uint64_t room = s.dst_cap - base;
 	uint32_t emit = len;
-	if (pos + len > s.dst_cap) emit = (uint32_t) (s.dst_cap - pos);
+	if ((uint64_t) off + len > room) emit = (uint64_t) off < room ? (uint32_t) (room - off) : 0u;
 	if (lane < nq && emit < len) {
-		bm->scratch[5] = len - emit;
-		bm->scratch[6] = dist;
+		pend[0] = len - emit;
+		pend[1] = dist;
 	}
-	const bool dependent = is_match && ((int64_t) pos - (int64_t) dist + (int64_t) len > (int64_t) base || dist < len);
+	const uint64_t done = (uint64_t) total > room ? s.dst_cap : base + total;
+	/* the ring will hold [done - RING, done): what is older comes from L2 */
+	{
+		const int64_t lo = (int64_t) done - (int64_t) RING;
+		if (lo > s.ring_lo) s.ring_lo = lo;
+	}
+	const int64_t src = (int64_t) base + (int64_t) off - (int64_t) dist;
+	const bool dependent = is_match && (src + (int64_t) len > (int64_t) base || dist < len);
 	const bool longm = is_match && !dependent && emit > 16;
-	if (lane < nq && !is_match) put_byte(s, pos, (uint8_t) q);
+	const uint32_t wi = ring_index(s, (uint32_t) base + off);
+	if (lane < nq && !is_match && emit) s.ring[wi] = (uint8_t) q;
 	if (is_match && !dependent && !longm) {
-		/* short far match: all loads first, then the stores */
-		uint8_t tmp[16];
+		/* short match from older bytes */
+		if (src >= s.ring_lo) {
+			const uint32_t ri = ring_index(s, (uint32_t) src);
+			for (uint32_t j = 0; j < emit; j++) s.ring[(wi + j) & (RING - 1u)] = s.ring[(ri + j) & (RING - 1u)];
+		} else if (src >= 0 && src + (int64_t) emit <= s.ring_lo) {
+			/* all of it in L2: the (up to five) aligned words that hold the source bytes are
+			 * loaded together -- one round trip instead of one per byte */
+			const uint8_t* const g = s.dst + src;
+			const uint32_t* const gw = (const uint32_t*) ((uintptr_t) g & ~(uintptr_t) 3);
+			const uint32_t sh = (uint32_t) ((uintptr_t) g & 3u);
+			const uint32_t nw = (sh + emit + 3u) >> 2;
+			uint32_t w[5];
 #pragma unroll
-		for (int j = 0; j < 16; j++)
-			if ((uint32_t) j < emit) tmp[j] = out_byte(s, (int64_t) (pos - dist) + j);
+			for (uint32_t k = 0; k < 5; k++) w[k] = k < nw ? __ldcg(gw + k) : 0u;
+			uint32_t x[4];
 #pragma unroll
-		for (int j = 0; j < 16; j++)
-			if ((uint32_t) j < emit) put_byte(s, pos + j, tmp[j]);
+			for (uint32_t k = 0; k < 4; k++) x[k] = __funnelshift_r(w[k], w[k + 1], 8u * sh);
+#pragma unroll
+			for (uint32_t j = 0; j < 16; j++)
+				if (j < emit) s.ring[(wi + j) & (RING - 1u)] = (uint8_t) (x[j >> 2] >> (8u * (j & 3u)));
+		} else {
+			for (uint32_t j = 0; j < emit; j++) s.ring[(wi + j) & (RING - 1u)] = out_byte(s, src + j);
+		}
 	}
+	/* cooperative copies: the long ones, then -- in order -- the ones that depend on this group */
 	unsigned lm = __ballot_sync(JDB_FULL_MASK, longm);
-	while (lm) {
-		int src = __ffs(lm) - 1;
-		lm &= lm - 1;
-		uint64_t p2 = __shfl_sync(JDB_FULL_MASK, pos, src);
-		uint32_t l2 = __shfl_sync(JDB_FULL_MASK, emit, src);
-		uint32_t d2 = __shfl_sync(JDB_FULL_MASK, dist, src);
-		copy_match(s, p2, l2, d2);
-	}
+	unsigned dm = __ballot_sync(JDB_FULL_MASK, dependent && emit);
 	__syncwarp();
-	unsigned dm = __ballot_sync(JDB_FULL_MASK, dependent);
-	while (dm) {
-		int src = __ffs(dm) - 1;
-		dm &= dm - 1;
-		uint64_t p2 = __shfl_sync(JDB_FULL_MASK, pos, src);
-		uint32_t l2 = __shfl_sync(JDB_FULL_MASK, emit, src);
-		uint32_t d2 = __shfl_sync(JDB_FULL_MASK, dist, src);
-		copy_match(s, p2, l2, d2);
+	while (lm | dm) {
+		int from;
+		if (lm) { from = __ffs(lm) - 1; lm &= lm - 1; }
+		else { from = __ffs(dm) - 1; dm &= dm - 1; }
+		const uint32_t w2 = __shfl_sync(JDB_FULL_MASK, wi, from);
+		const uint32_t l2 = __shfl_sync(JDB_FULL_MASK, emit, from);
+		const uint32_t d2 = __shfl_sync(JDB_FULL_MASK, dist, from);
+		const int64_t s2 = __shfl_sync(JDB_FULL_MASK, (long long) src, from);
+		/* every source byte lies before the match (k < dist) */
+		for (uint32_t j = lane; j < l2; j += 32) {
+			const uint32_t k = d2 >= l2 ? j : j % d2;
+			s.ring[(w2 + j) & (RING - 1u)] = out_byte(s, s2 + k);
+		}
 		__syncwarp();
 	}
-	uint64_t done = base + total;
-	if (done > s.dst_cap) {
-		done = s.dst_cap;
-		pend_len = bm->scratch[5];
-		pend_dist = bm->scratch[6];
+	if ((uint64_t) total > room) {
+		pend_len = pend[0];
+		pend_dist = pend[1];
 	}
 	s.out = done;
-	__syncwarp();
+	flush_ring(s, done, false);
+	return nq;
+}
+
+/*
+ * One lane's share of a lane-parallel round: decode symbols from bit `start` until the
+ * position reaches `limit` (symbols START before the limit; the last one may end behind it),
+ * writing tokens to this lane's slots.  Purely speculative: it judges nothing.  Whatever
+ * is not a plain literal / length+distance / end-of-block stops the lane with PF_ANOM at
+ * the position of that symbol, and the step-by-step decoder decides what it means.
+ * The caller guarantees 64 readable bits behind `limit`.
+ */
+struct LaneRun {
+	uint32_t start, end, n, bytes, flag;
+	int32_t  need;          /* max over matches of (distance - bytes this lane produced before it) */
+};
+
+static __device__ LANE_INLINE void
+lane_decode(const WarpMem* m, uint32_t* slots, LaneRun& r, uint32_t start, uint32_t limit, uint32_t safe_end)
+{
+	uint32_t pos = start, n = 0, bytes = 0, flag = PF_OK;
+	int32_t need = 0;
+	while (pos < limit) {
+		if (n >= PQ_K) { flag = PF_FULL; break; }
+		const uint32_t bits = peek32(m->inbuf, pos);
+		const uint32_t e = lookup32(m->lit, bits, LIT_ROOT);
+		const uint32_t nb = e & 15u;
+		const uint32_t type = (e >> 8) & 3u;
+		uint32_t tok;
+		if (nb == 0) { flag = PF_ANOM; break; }
+		if (type == T_LIT) {
+			tok = e >> 16;
+			pos += nb;
+			bytes += 1;
+		} else if (type == T_BASE) {
+			if ((e >> 16) == 0) { flag = PF_ANOM; break; }
+			const uint32_t lxb = (e >> 4) & 15u;
+			const uint32_t len = (e >> 16) + ((bits >> nb) & ((1u << lxb) - 1u));
+			const uint32_t o2 = pos + nb + lxb;
+			const uint32_t bits2 = peek32(m->inbuf, o2);
+			const uint32_t d = lookup32(m->dist, bits2, DIST_ROOT);
+			const uint32_t dnb = d & 15u, dxb = (d >> 4) & 15u;
+			if (dnb == 0 || (d >> 16) == 0) { flag = PF_ANOM; break; }
+			const uint32_t dist = (d >> 16) + ((bits2 >> dnb) & ((1u << dxb) - 1u));
+			const int32_t nd = (int32_t) dist - (int32_t) bytes;
+			if (nd > need) need = nd;
+			tok = (len << 16) | dist;
+			pos = o2 + dnb + dxb;
+			bytes += len;
+		} else {
+			/* T_EOB (T_SUB never comes out of a two-level look-up) */
+			pos += nb;
+			flag = PF_EOB;
+			break;
+		}
+		slots[n * 32u] = tok;
+		n++;
+	}
+	if (flag == PF_OK && limit == safe_end) flag = PF_STOP;
+	r.start = start; r.end = pos; r.n = n; r.bytes = bytes; r.flag = flag; r.need = need;
 }
 
 /*
@@ -581,6 +699,8 @@ inflate_stream(WarpMem* m, Stream& s)
 	s.total_before = 0;
 	s.ring = m->ring;
 	s.ring_lo = 0;
+	s.rbase = (uint32_t) (uintptr_t) s.dst;
+	s.flushed = 0;
 
 	if (s.st) {
 		jdb_inflate_state* st = s.st;
@@ -601,16 +721,8 @@ inflate_stream(WarpMem* m, Stream& s)
 		}
 	}
 
-	/* finish a match that did not fit into the previous target window */
-	if (pend_len) {
-		uint32_t n = pend_len;
-		if ((uint64_t) n > s.dst_cap) n = (uint32_t) s.dst_cap;
-		copy_match(s, 0, n, pend_dist);
-		__syncwarp();
-		s.out = n;
-		pend_len -= n;
-		if (pend_len) { s.status = ST_TGTEXH; goto finish; }
-	}
+	/* (a match that did not fit into the previous target window is finished by the first
+	 * round of the symbol loop: pend_len != 0 implies phase == JDB_INF_SYMBOLS) */
 
 	for (;;) {
 		/* ---------------- block header ---------------- */
@@ -654,8 +766,18 @@ inflate_stream(WarpMem* m, Stream& s)
 			uint64_t srcleft = s.src_len - pos, dstleft = s.dst_cap - s.out;
 			if (n > srcleft) n = srcleft;
 			if (n > dstleft) n = dstleft;
-			if (!s.count_only)
-				for (uint64_t j = lane; j < n; j += 32) put_byte(s, s.out + j, s.src[pos + j]);
+			if (!s.count_only) {
+				/* straight to the target, and into the ring for the matches of later blocks */
+				flush_ring(s, s.out, true);
+				for (uint64_t j = lane; j < n; j += 32) {
+					const uint8_t v = s.src[pos + j];
+					s.dst[s.out + j] = v;
+					s.ring[ring_index(s, (uint32_t) (s.out + j))] = v;
+				}
+				s.flushed = s.out + n;
+				const int64_t lo = (int64_t) (s.out + n) - (int64_t) RING;
+				if (lo > s.ring_lo) s.ring_lo = lo;
+			}
 			__syncwarp();
 			s.out += n;
 			const bool empty_block = stored_left == 0;
@@ -706,10 +828,14 @@ inflate_stream(WarpMem* m, Stream& s)
 			uint32_t o = pre ? 8u * c + 8u - b.bc : 8u * al;
 			uint32_t filled = 0;
 
+			uint32_t S = PAR_S0;              /* subsequence length of the lane-parallel rounds */
+			bool step_by_step = false;        /* the next batch goes through the step-by-step decoder */
 			for (;;) {
-				/* ---- all lanes: keep >= 3 KiBit of input ahead of `o` in the ring ---- */
+				/* ---- all lanes: keep the input of one lane-parallel round (or >= 3 KiBit) ahead
+				 * of `o` in the ring ---- */
+				const uint32_t ahead = 32u * S + 64u > 3072u ? 32u * S + 64u : 3072u;
 				if (o >= filled) filled = o & ~1023u;
-				while (filled < o + 3072u && filled < fill_limit) {
+				while (filled < o + ahead && filled < fill_limit) {
 					const uint32_t k = (filled >> 5) + lane;
 					uint32_t v = 0;
 					if (k < nwords) {
@@ -722,10 +848,120 @@ inflate_stream(WarpMem* m, Stream& s)
 				}
 				__syncwarp();
 
+				/* ---- lane-parallel round --------------------------------------------------
+				 * Lane l decodes the symbols that start in bits [o + l*S, o + (l+1)*S) of the
+				 * window.  Only lane 0 knows where its first symbol starts; the others guess
+				 * (their subsequence boundary), and a Huffman decoder that starts at a wrong
+				 * bit falls into step with the true symbol sequence after a few symbols.  So:
+				 * all lanes decode; then every lane whose predecessor ended somewhere else than
+				 * where it started decodes again from there, until nothing changes.  Lane 0 is
+				 * right by construction, a lane that started where a right lane ended is right:
+				 * the chain of agreeing lanes from lane 0 on is the decoded symbol sequence,
+				 * whatever the others did.  The round judges nothing: anything but a plain
+				 * literal / match / end of block inside the chain ends the chain there and the
+				 * step-by-step decoder below takes the next batch from that bit, so every status
+				 * and error decision stays in one place. */
+				uint32_t gtok = 0, gbytes = 0;       /* tokens in m->cq for the emission below, and their bytes */
+				ev = 0;
+				if (pend_len) {
+					/* the rest of a match the previous target window cut */
+					if (lane == 0) m->cq[0] = (pend_len << 16) | pend_dist;
+					gtok = 1;
+					gbytes = pend_len;
+					pend_len = 0;
+				} else
+#ifndef PAR_OFF
+				if (!step_by_step && endbit - o >= 2u * S + 64u) {
+					const uint32_t safe_end = endbit - 64u;
+					const uint64_t room64 = s.dst_cap - s.out;
+					const uint32_t room = room64 > 0xfffff000ull ? 0xfffff000u : (uint32_t) room64;
+					const uint64_t reach64 = s.out + s.hist_avail;
+					const uint32_t reach = reach64 > 0x10000ull ? 0x10000u : (uint32_t) reach64;
+					uint32_t* const slots = m->cq + lane;
+					uint32_t lim = o + (lane + 1u) * S;
+					if (lim > safe_end) lim = safe_end;
+					LaneRun r;
+					{
+						uint32_t st = o + lane * S;
+						if (st > safe_end) st = safe_end;
+						bool run = true;
+						for (int pass = 0; ; pass++) {
+							if (run) lane_decode(m, slots, r, st, lim, safe_end);
+							if (pass + 1 >= PAR_MAXPASS) break;
+							const uint32_t pe = __shfl_up_sync(JDB_FULL_MASK, r.end, 1);
+							const uint32_t pf = __shfl_up_sync(JDB_FULL_MASK, r.flag, 1);
+							run = lane > 0 && pf == PF_OK && pe != r.start;
+							if (!__any_sync(JDB_FULL_MASK, run)) break;
+							st = pe;
+						}
+					}
+					/* the chain: lanes 0..v */
+					uint32_t v;
+					{
+						const uint32_t pe = __shfl_up_sync(JDB_FULL_MASK, r.end, 1);
+						const uint32_t pf = __shfl_up_sync(JDB_FULL_MASK, r.flag, 1);
+						const bool linked = lane == 0 || (pf == PF_OK && pe == r.start);
+						const unsigned broken = __ballot_sync(JDB_FULL_MASK, !linked);
+						v = broken ? (uint32_t) __ffs(broken) - 1u : 32u;      /* lanes 0..v-1 are in the chain */
+					}
+					/* bytes in front of every lane; the target room and the reach of the distances
+					 * may cut the chain short (the step-by-step decoder finds out exactly where) */
+					uint32_t bincl = lane < v ? r.bytes : 0u;
+					uint32_t nincl = lane < v ? r.n : 0u;
+					for (int k = 1; k < 32; k <<= 1) {
+						const uint32_t tb = __shfl_up_sync(JDB_FULL_MASK, bincl, k);
+						const uint32_t tn = __shfl_up_sync(JDB_FULL_MASK, nincl, k);
+						if ((int) lane >= k) { bincl += tb; nincl += tn; }
+					}
+					{
+						const bool bad = lane < v && (bincl > room || (int64_t) r.need > (int64_t) reach + (int64_t) (bincl - r.bytes));
+						const unsigned cut = __ballot_sync(JDB_FULL_MASK, bad);
+						if (cut) {
+							v = (uint32_t) __ffs(cut) - 1u;
+							step_by_step = true;
+						}
+					}
+					uint32_t ntok = 0, nbytes = 0, lastflag = PF_OK, newo = o;
+					if (v) {
+						ntok = __shfl_sync(JDB_FULL_MASK, nincl, (int) v - 1);
+						nbytes = __shfl_sync(JDB_FULL_MASK, bincl, (int) v - 1);
+						lastflag = __shfl_sync(JDB_FULL_MASK, r.flag, (int) v - 1);
+						newo = __shfl_sync(JDB_FULL_MASK, r.end, (int) v - 1);
+					}
+					/* next round: shorter subsequences when the token slots ran out, longer ones
+					 * again when they stay half empty */
+					{
+						const unsigned full = __ballot_sync(JDB_FULL_MASK, lane < v && r.flag == PF_FULL);
+						const uint32_t maxn = __reduce_max_sync(JDB_FULL_MASK, lane < v ? r.n : 0u);
+						if (full) S = S >= PAR_SMIN + 32u ? S - 32u : PAR_SMIN;
+						else if (maxn <= PQ_K / 2u && S < PAR_SMAX) S += 32u;
+					}
+					if (ntok && !s.count_only) {
+						/* compact the tokens of the chain: through registers, in place */
+						uint32_t t[PQ_K];
+						const uint32_t mine = lane < v ? r.n : 0u;
+						const uint32_t at = nincl - mine;
+#pragma unroll
+						for (uint32_t i = 0; i < PQ_K; i++)
+							if (i < mine) t[i] = slots[i * 32u];
+						__syncwarp();
+#pragma unroll
+						for (uint32_t i = 0; i < PQ_K; i++)
+							if (i < mine) m->cq[at + i] = t[i];
+					}
+					ev = lastflag == PF_EOB ? 1u : 0u;
+					if (lastflag == PF_ANOM || newo == o) step_by_step = true;
+					o = newo;
+					gtok = ntok;
+					gbytes = nbytes;
+				} else
+#endif
+				{
+				step_by_step = false;
+
 				/* ---- decode up to QUEUE symbols (uniform; lane 0 writes the queue) ---- */
 				uint32_t nq = 0;
 				uint32_t qbytes = 0;
-				ev = 0;
 				{
 					/* everything in 32 bits: a queue never holds more than MAXBATCH + 258 bytes */
 					const uint64_t room64 = s.dst_cap - s.out;
@@ -743,7 +979,7 @@ inflate_stream(WarpMem* m, Stream& s)
 						if (((e >> 8) & 3u) == T_LIT) {
 							if (nb - 1u < avail && qbytes < room) {
 								o += nb;
-								if (lane == 0) m->queue[nq] = e >> 16;
+								if (lane == 0) m->cq[nq] = e >> 16;
 								nq++;
 								qbytes++;
 								continue;
@@ -759,7 +995,7 @@ inflate_stream(WarpMem* m, Stream& s)
 							const uint32_t fo3 = fo2 + dnb + dxb;
 							if (dnb != 0 && (fd >> 16) != 0 && fo3 <= endbit && fdist <= reach + qbytes && qbytes + flen <= room) {
 								o = fo3;
-								if (lane == 0) m->queue[nq] = (flen << 16) | fdist;
+								if (lane == 0) m->cq[nq] = (flen << 16) | fdist;
 								nq++;
 								qbytes += flen;
 								continue;
@@ -775,7 +1011,7 @@ inflate_stream(WarpMem* m, Stream& s)
 						if (type == T_LIT) {
 							if (qbytes >= room) { ev = 3; break; }
 							o += nb;
-							if (lane == 0) m->queue[nq] = e >> 16;    /* len field 0: literal */
+							if (lane == 0) m->cq[nq] = e >> 16;    /* len field 0: literal */
 							nq++;
 							qbytes++;
 							continue;
@@ -805,18 +1041,30 @@ inflate_stream(WarpMem* m, Stream& s)
 						if (dist > reach + qbytes) { o = o2; ev = 4 + E_FAROFFSET; break; }
 						if (qbytes >= room) { ev = 3; break; }
 						o = o2;
-						if (lane == 0) m->queue[nq] = (len << 16) | dist;       /* len <= 258, dist <= 32768 */
+						if (lane == 0) m->cq[nq] = (len << 16) | dist;       /* len <= 258, dist <= 32768 */
 						nq++;
 						qbytes += len;
 						if (qbytes > room) { ev = 3; break; }        /* partially fits: split below */
 					}
 				}
+				gtok = nq;
+				gbytes = qbytes;
+				}
 				__syncwarp();
 
-				/* ---- all lanes: turn the queue into bytes ---- */
-				if (nq) {
-					if (s.count_only) s.out += qbytes;
-					else emit_queue(s, &m->bm, m->queue, nq, pend_len, pend_dist);
+				/* ---- all lanes: turn the tokens into bytes ---- */
+				__syncwarp();
+				if (gtok) {
+					if (s.count_only) {
+						const uint64_t room64 = s.dst_cap - s.out;
+						s.out += gbytes < room64 ? gbytes : room64;
+					} else {
+						for (uint32_t done = 0; done < gtok; ) {
+							const uint32_t take = gtok - done < 32u ? gtok - done : 32u;
+							done += emit_queue(s, m->pend, m->cq + done, take, pend_len, pend_dist);
+						}
+					}
+					if (pend_len) ev = 3;
 				}
 				if (ev) break;
 			}
@@ -840,7 +1088,7 @@ inflate_stream(WarpMem* m, Stream& s)
 		}
 	}
 
-finish:
+	if (!s.count_only) flush_ring(s, s.out, true);
 	/* a starved final input is an error (src/inflator.c:810-816, 838-842) */
 	if (s.status == ST_SRCEXH && s.final) {
 		s.status = ST_ERROR;

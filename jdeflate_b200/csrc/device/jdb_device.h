@@ -95,7 +95,9 @@ int jdb_checksum(const uint8_t* data, size_t n, int which,
 
 /* ---- inflate (inflate.cu) ---------------------------------------------- */
 #define JDB_INFLATE_HISTORY 32768u     /* DEFLATE window, power of two */
-#define JDB_INF_LIT_TABLE   1344       /* >= ENOUGHL 1332 (root 10), reference src/inflator.c:35-48 */
+#define JDB_INF_LIT_ROOT    9          /* the reference uses 10 (LROOTBITS, src/inflator.c:30): 9 halves the table, which
+                                        * buys a 4 KiB output ring per warp at 16 warps per SM */
+#define JDB_INF_LIT_TABLE   864        /* >= 852 = zlib's ENOUGH for 286 symbols, root 9, 15-bit codes */
 #define JDB_INF_DIST_TABLE  416        /* >= ENOUGHD 400  (root 8),  reference src/inflator.c:50-62 */
 
 enum { JDB_INF_HEADER = 0, JDB_INF_STORED = 1, JDB_INF_SYMBOLS = 2 };

@@ -87,6 +87,11 @@ ck_run(int which, uint32 value, const uint8* source, uintxx size)
 		uintxx n = left;
 		const uint8* d = p;
 
+		/* one launch covers at most 1 GiB: the kernels count vectors and combine lengths in
+		 * 32 bits (the running value in device memory chains the launches) */
+		if (n > ((uintxx) 1 << 30)) {
+			n = (uintxx) 1 << 30;
+		}
 		if (!ondevice) {
 			if (n > CK_STAGE_BYTES) {
 				n = CK_STAGE_BYTES;

@@ -17,6 +17,7 @@
 #include <string.h>
 #include <stddef.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include "jdb_host.h"
 #include "jdb_internal.h"
 
@@ -81,6 +82,8 @@ struct TINFLTPrvt {
 	size_t readahead;       /* zstrm: the caller signals the end of the input with `final`, so a chain under way may
 	                         * wait for this much input before the next step (a step takes as long as its slowest chunk) */
 	size_t par_want;        /* queued bytes the next step of a chain waits for */
+	size_t leftover;        /* bytes after the end of the stream that came from earlier source windows: they
+	                         * sit at inq[inqoff ..) until zstrm takes them back or the next reset */
 	jdb_dbuf   outbuf;
 
 	jdb_inflate_state* dstate;
@@ -174,6 +177,7 @@ inflator_reset(TInflator* state)
 	PRVT->done = 0;
 	PRVT->inqoff = 0;
 	PRVT->inqlen = 0;
+	PRVT->leftover = 0;
 	PRVT->par_ok = 1;
 	PRVT->par_total = 0;
 	PRVT->par_nfrag = PRVT->par_cur = PRVT->par_off = PRVT->par_fin = PRVT->par_starved = 0;
@@ -267,6 +271,37 @@ jdb_inflator_set_readahead(TInflator* state, size_t bytes)
 	PRVT->readahead = bytes;
 }
 
+/* zstrm: the memory of the last source window is gone (its read buffer was reused): nothing
+ * can be handed back through it any more */
+void
+jdb_inflator_drop_window(TInflator* state)
+{
+	PBLC->sbgn = PBLC->source = PBLC->send;
+}
+
+/* Bytes behind the end of the stream that the public source window cannot give back because
+ * they were queued from earlier windows (zstrm's read-ahead): zstrm takes them back from here. */
+size_t
+jdb_inflator_leftover(TInflator* state)
+{
+	return PRVT->done ? PRVT->leftover : 0;
+}
+
+int
+jdb_inflator_take_leftover(TInflator* state, uint8* dst)
+{
+	jdb_rt_use_device(PRVT->device);
+	if (PRVT->leftover == 0) {
+		return 0;
+	}
+	if (jdb_copy_async(dst, PRVT->inq.ptr + PRVT->inqoff, PRVT->leftover, PRVT->stream) != JDB_OK ||
+	    jdb_stream_sync(PRVT->stream) != JDB_OK) {
+		return -1;
+	}
+	PRVT->leftover = 0;
+	return 0;
+}
+
 int
 jdb_inflator_get_checks(TInflator* state, uint32* crc, uint32* adler)
 {
@@ -310,24 +345,41 @@ static int
 absorb(struct TINFLTPrvt* state)
 {
 	size_t avail = (size_t) (PBLC->send - PBLC->source);
-	size_t room;
+	size_t room, want;
 
 	if (avail == 0) {
 		return 0;
 	}
-	if (PRVT->inqlen == 0) {
-		/* reserve() drops the old contents: growing is only legal while the queue
-		 * is empty.  Large windows get a large queue so that a parallel step sees
-		 * many chunks at once. */
-		size_t want = PRVT->inqcap ? PRVT->inqcap : INQ_BYTES;
-		while (want < avail && want < INQ_MAX) {
-			want *= 2;
+	/* Large windows get a large queue so that a parallel step sees many chunks at once; so
+	 * does a chain of small windows that gathers input for its next step (par_want). */
+	want = PRVT->inqcap ? PRVT->inqcap : INQ_BYTES;
+	while (want < PRVT->inqlen + avail && want < INQ_MAX) {
+		want *= 2;
+	}
+	if (want > PRVT->inqcap || PRVT->inq.ptr == NULL) {
+		if (PRVT->inqlen == 0) {
+			if (jdb_dbuf_reserve(&PRVT->inq, want) != 0) {
+				return -1;
+			}
+			PRVT->inqcap = want;
+			PRVT->inqoff = 0;
 		}
-		if (jdb_dbuf_reserve(&PRVT->inq, want) != 0) {
-			return -1;
+		else {
+			/* the queue holds bytes: they move to the front of a larger one */
+			jdb_dbuf bigger = { NULL, 0 };
+			if (jdb_dbuf_reserve(&bigger, want) == 0) {
+				if (jdb_copy_async(bigger.ptr, PRVT->inq.ptr + PRVT->inqoff, PRVT->inqlen, PRVT->stream) != JDB_OK ||
+				    jdb_stream_sync(PRVT->stream) != JDB_OK) {
+					jdb_dbuf_release(&bigger);
+					return -1;
+				}
+				jdb_dbuf_release(&PRVT->inq);
+				PRVT->inq = bigger;
+				PRVT->inqcap = want;
+				PRVT->inqoff = 0;
+			}
+			/* else: no memory for a larger queue -- the caller works with the one there is */
 		}
-		PRVT->inqcap = want;
-		PRVT->inqoff = 0;
 	}
 	if (PRVT->inq.ptr == NULL) {
 		return -1;
@@ -593,6 +645,10 @@ parallel_step(struct TINFLTPrvt* state)
 	}
 	PRVT->par_nfrag = nfrag;
 	PRVT->par_fin = (uint32) fin;
+	if (getenv("JDB200_TRACE")) {
+		fprintf(stderr, "parallel_step: queued %zu starts %u frags %u used %llu out %llu starved %u want %zu cap %zu\n",
+		        n, ns, nfrag, (unsigned long long) used, (unsigned long long) total, PRVT->par_starved, PRVT->par_want, PRVT->inqcap);
+	}
 	return 1;
 }
 
@@ -726,9 +782,15 @@ inflator_inflate(TInflator* state, uint32 final)
 				/* zstrm feeds a chain of chunks and promises `final` at the end of its input:
 				 * gather more of it, a step over many chunks takes no longer than one over few */
 				if (absorbed_all) {
+					/* the caller may reuse its window the moment this returns: the copy into
+					 * the queue has to be over */
+					if (jdb_stream_sync(PRVT->stream) != JDB_OK) {
+						poison(PRVT, INFLT_EBADSTATE);
+						return INFLT_ERROR;
+					}
 					return (eINFLTResult) (PBLC->status = INFLT_SRCEXHSTD);
 				}
-				continue;
+				step = 1;               /* the queue is full and cannot grow: work with what it holds */
 			}
 			if (!step && PRVT->par_starved) {
 				/* a streaming caller with small windows: the last step stopped because the
@@ -738,6 +800,10 @@ inflator_inflate(TInflator* state, uint32 final)
 				 * of somebody else's stream -- the sequential decoder decides. */
 				if (PRVT->inqlen == PRVT->par_seen) {
 					if (absorbed_all && !PBLC->finalinput) {
+						if (jdb_stream_sync(PRVT->stream) != JDB_OK) {
+							poison(PRVT, INFLT_EBADSTATE);
+							return INFLT_ERROR;
+						}
 						return (eINFLTResult) (PBLC->status = INFLT_SRCEXHSTD);
 					}
 				}
@@ -842,6 +908,8 @@ L_DELIVER:
 					giveback = window;
 				}
 				PBLC->source -= giveback;
+				/* what came from earlier windows stays in the queue: jdb_inflator_leftover() */
+				PRVT->leftover = PRVT->inqlen - giveback;
 				PRVT->inqlen = 0;
 				PRVT->done = 1;
 				PBLC->state = POISON;

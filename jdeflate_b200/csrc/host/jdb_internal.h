@@ -15,5 +15,9 @@ int  jdb_deflator_get_checks(TDeflator* d, uint32* crc, uint32* adler);
 void jdb_inflator_set_checks(TInflator* s, int which);
 void jdb_inflator_set_readahead(TInflator* s, size_t bytes);
 int  jdb_inflator_get_checks(TInflator* s, uint32* crc, uint32* adler);
+/* compressed bytes queued from earlier source windows that lie beyond the end of the stream */
+void   jdb_inflator_drop_window(TInflator* s);
+size_t jdb_inflator_leftover(TInflator* s);
+int    jdb_inflator_take_leftover(TInflator* s, uint8* dst);
 
 #endif

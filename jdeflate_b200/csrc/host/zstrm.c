@@ -18,6 +18,8 @@
  */
 #include <jdeflate/zstrm.h>
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "jdb_host.h"
 #include "jdb_internal.h"
 
@@ -53,10 +55,17 @@ struct TZStrmPrvt {
 	const uint8* sbgn;
 	const uint8* send;
 	const uint8* wbase;     /* start of the window the inflator currently holds */
+	const uint8* wend;      /* ... and its end (members after the first get part of what was read) */
 	uintxx wused;           /* inflator_srcend() at the previous call           */
 	/* inflate: decoded bytes waiting in obuf for the caller */
 	uint8* pbgn;
 	uint8* pend;
+
+	/* inflate: gzip members (RFC 1952 2.2: a file is a series of members) */
+	uintxx mbase;           /* public.total at the start of the current member */
+	uint32 members;         /* members finished so far */
+	uintxx mwindow;         /* members after the first are fed in growing windows */
+	uint8* lbuf;            /* compressed bytes the inflator had queued beyond the end of a member */
 
 	uint8* ibuf;            /* page-locked, ZS_IOBYTES: callback reads / deflate output */
 	uint8* obuf;            /* page-locked, ZS_IOBYTES: read-ahead of decoded bytes     */
@@ -65,7 +74,7 @@ struct TZStrmPrvt {
 };
 
 #define ZS ((struct TZStrmPrvt*) (uintptr_t) state)
-#define SETERROR(E) (zstrm->public.error = (E))
+#define SETERROR(E) (zstrm->public.error = (E), (getenv("JDB200_TRACE") ? fprintf(stderr, "zstrm error %d at line %d\n", (int) (E), __LINE__) : 0))
 #define SETSTATE(S) (zstrm->public.state = (S))
 
 static void
@@ -168,6 +177,7 @@ zstrm_destroy(const TZStrm* state)
 	}
 	jdb_pinned_free(zstrm->ibuf);
 	jdb_pinned_free(zstrm->obuf);
+	free(zstrm->lbuf);
 	zstrm->allctr->dispose(zstrm, sizeof(struct TZStrmPrvt), zstrm->allctr->user);
 }
 
@@ -198,6 +208,11 @@ zstrm_reset(const TZStrm* state)
 	zstrm->result = 0;
 	zstrm->srcset = 0;
 	zstrm->srceof = 0;
+	zstrm->mbase = 0;
+	zstrm->members = 0;
+	zstrm->mwindow = 0;
+	free(zstrm->lbuf);
+	zstrm->lbuf = NULL;
 	if (zstrm->public.smode == ZSTRM_INFLATE) {
 		zstrm->doadler = (zstrm->public.flags & ZSTRM_DOADLER) != 0;
 		zstrm->docrc   = (zstrm->public.flags & ZSTRM_DOCRC)   != 0;
@@ -449,8 +464,10 @@ checkgziptail(struct TZStrmPrvt* zstrm)
 	if (zstrm->public.error) {
 		return;
 	}
-	/* ISIZE is the size modulo 2^32 (RFC 1952) */
-	if (total != (uint32) zstrm->public.total) {
+	/* ISIZE is the size of this member modulo 2^32 (RFC 1952); the reference compares its
+	 * 64-bit total with the 32-bit field, src/zstrm.c:660-667, and so rejects members
+	 * of 4 GiB and more (DESIGN.md deviation 11) */
+	if (total != (uint32) (zstrm->public.total - zstrm->mbase)) {
 		SETERROR(ZSTRM_EBADDATA);
 	}
 }
@@ -503,12 +520,72 @@ syncchecks(struct TZStrmPrvt* zstrm)
 
 /* ---- inflate --------------------------------------------------------------- */
 
+/* With read-ahead the inflator queues several source windows before it decodes; what it
+ * holds beyond the end of the stream and cannot give back through its source window comes
+ * back here and is read (trailer, next member) before anything else. */
+static int
+takeleftover(struct TZStrmPrvt* zstrm)
+{
+	size_t lo = jdb_inflator_leftover(zstrm->infltr);
+	size_t rest = (size_t) (zstrm->send - zstrm->sbgn);
+	uint8* nb;
+
+	if (lo == 0) {
+		return 0;
+	}
+	nb = malloc(lo + rest + 1);
+	if (nb == NULL || jdb_inflator_take_leftover(zstrm->infltr, nb) != 0) {
+		free(nb);
+		return -1;
+	}
+	if (rest) {
+		memcpy(nb + lo, zstrm->sbgn, rest);
+	}
+	free(zstrm->lbuf);
+	zstrm->lbuf = nb;
+	zstrm->sbgn = nb;
+	zstrm->send = nb + lo + rest;
+	zstrm->public.usedinput -= lo;
+	return 0;
+}
+
+/* After a gzip trailer: does another member follow?  (The reference stops after the first
+ * member, src/zstrm.c:626-667; gzip(1) and zlib's gzread decode them all and ignore
+ * trailing bytes that are not a member.)  Leaves the read position in front of the header. */
+static int
+nextmember(struct TZStrmPrvt* zstrm)
+{
+	if (zstrm->public.error) {
+		return 0;
+	}
+	while ((size_t) (zstrm->send - zstrm->sbgn) < 2 && zstrm->iofn && !zstrm->srceof) {
+		/* keep the odd byte in front of what the callback gives */
+		size_t have = (size_t) (zstrm->send - zstrm->sbgn);
+		intxx r;
+		if (have) {
+			zstrm->ibuf[0] = zstrm->sbgn[0];
+		}
+		r = zstrm->iofn(zstrm->ibuf + have, ZS_IOBYTES - have, zstrm->user);
+		if (r < 0 || (uintxx) r > ZS_IOBYTES - have) {
+			SETERROR(ZSTRM_EIOERROR);
+			return 0;
+		}
+		if (r == 0) {
+			zstrm->srceof = 1;
+		}
+		zstrm->sbgn = zstrm->ibuf;
+		zstrm->send = zstrm->ibuf + have + r;
+	}
+	return (size_t) (zstrm->send - zstrm->sbgn) >= 2 && zstrm->sbgn[0] == 0x1f && zstrm->sbgn[1] == 0x8b;
+}
+
 /* decode into `buffer` (host or device memory); src/zstrm.c:792-958 */
 static uintxx
 inflate(struct TZStrmPrvt* zstrm, uint8* buffer, uintxx total)
 {
 	struct TInflator* infltr = zstrm->infltr;
 	uint8* bbgn = buffer;
+	uint8* bcnt = buffer;       /* bytes before this are in public.total already */
 	uintxx n;
 
 	while (total) {
@@ -541,22 +618,40 @@ inflate(struct TZStrmPrvt* zstrm, uint8* buffer, uintxx total)
 		if (zstrm->result == INFLT_OK) {
 			/* end of the DEFLATE stream: everything the inflator did not use is
 			 * still ours (exact accounting), the trailer follows */
-			if (syncchecks(zstrm) != 0) {
+			if (takeleftover(zstrm) != 0 || syncchecks(zstrm) != 0) {
 				fail(zstrm, ZSTRM_EOOM);
 				break;
 			}
 			if (zstrm->docrc) {
 				zstrm->public.crc ^= 0xffffffffu;
 			}
-			n = (uintxx) (buffer - bbgn);
-			zstrm->public.total += n;
+			zstrm->public.total += (uintxx) (buffer - bcnt);
+			bcnt = buffer;
 			switch (zstrm->public.stype) {
 				case ZSTRM_GZIP: checkgziptail(zstrm); break;
 				case ZSTRM_ZLIB: checkzlibtail(zstrm); break;
 				default: break;
 			}
+			if (zstrm->public.stype == ZSTRM_GZIP && nextmember(zstrm)) {
+				/* the next member of the file: new header, new CRC-32, new ISIZE */
+				zstrm->members++;
+				zstrm->mbase = zstrm->public.total;
+				zstrm->mwindow = ZS_DIRECT;
+				zstrm->public.crc = 0xffffffffu;
+				parsegziphead(zstrm);
+				if (zstrm->public.error) {
+					SETSTATE(ZSTRM_END);
+					return (uintxx) (buffer - bbgn);
+				}
+				inflator_reset(infltr);
+				jdb_inflator_set_checks(infltr, checkmask(zstrm));
+				jdb_inflator_set_readahead(infltr, ZS_READAHEAD);
+				zstrm->result = INFLT_TGTEXHSTD;
+				zstrm->srcset = 0;
+				continue;
+			}
 			SETSTATE(ZSTRM_END);
-			return n;
+			return (uintxx) (buffer - bbgn);
 		}
 		if (zstrm->result == INFLT_ERROR) {
 			fail(zstrm, ZSTRM_EDEFLATE);
@@ -591,12 +686,29 @@ inflate(struct TZStrmPrvt* zstrm, uint8* buffer, uintxx total)
 				break;
 			}
 			if (zstrm->send != zstrm->sbgn) {
-				inflator_setsrc(infltr, zstrm->sbgn, (uintxx) (zstrm->send - zstrm->sbgn));
+				uintxx window = (uintxx) (zstrm->send - zstrm->sbgn);
+				if (zstrm->mwindow) {
+					/* a file of many small members: do not ship the whole buffer to the
+					 * device for each of them */
+					if (window > zstrm->mwindow) {
+						window = zstrm->mwindow;
+					}
+					zstrm->mwindow *= 2;
+				}
+				inflator_setsrc(infltr, zstrm->sbgn, window);
 				zstrm->wbase = zstrm->sbgn;
+				zstrm->wend = zstrm->sbgn + window;
 				zstrm->wused = 0;
 			}
-			/* else: the end of the input; the inflator keeps its (used up) window and is told
-			 * `final` below -- it may have been gathering input for a chunk-parallel step */
+			else {
+				/* the end of the input: the inflator is told `final` below -- it may have been
+				 * gathering input for a chunk-parallel step.  Its last window is used up and
+				 * the memory behind it is no longer that window. */
+				jdb_inflator_drop_window(infltr);
+				zstrm->wbase = zstrm->sbgn;
+				zstrm->wend = zstrm->send;
+				zstrm->wused = 0;
+			}
 			zstrm->srcset = 1;
 		}
 
@@ -612,7 +724,8 @@ inflate(struct TZStrmPrvt* zstrm, uint8* buffer, uintxx total)
 			cap = ZS_IOBYTES;
 		}
 		inflator_settgt(infltr, tgt, cap);
-		zstrm->result = inflator_inflate(infltr, zstrm->srceof ? 1 : 0);
+		/* `final` once the source is dry and the inflator's window ends where the read bytes end */
+		zstrm->result = inflator_inflate(infltr, zstrm->srceof && zstrm->wend == zstrm->send ? 1 : 0);
 		n = inflator_tgtend(infltr);
 		if (zstrm->result == INFLT_ERROR && zstrm->srceof && infltr->error == INFLT_EINPUTEND && n == 0) {
 			/* the stream is longer than the input (the reference: the callback has nothing
@@ -648,8 +761,8 @@ inflate(struct TZStrmPrvt* zstrm, uint8* buffer, uintxx total)
 		}
 	}
 
+	zstrm->public.total += (uintxx) (buffer - bcnt);
 	n = (uintxx) (buffer - bbgn);
-	zstrm->public.total += n;
 	if (n && zstrm->public.state == ZSTRM_NORMAL) {
 		syncchecks(zstrm);
 	}

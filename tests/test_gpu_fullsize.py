@@ -290,3 +290,74 @@ def test_cross_decode_64mib_with_the_compiled_reference(jd, ref, corpus):
     assert (st, err, used) == (api.OK, 0, len(theirs))
     assert back == d
     assert len(ours) <= 1.03 * len(theirs)
+
+
+def test_gzip_member_of_more_than_4_gib(jd, corpus):
+    """a gzip member of 4 GiB + 5 MiB.  ISIZE is the size modulo 2^32 (RFC 1952),
+    `total` counts in 64 bits; the reference compares its 64-bit total with the 32-bit field
+    (src/zstrm.c:660-667) and would reject its own file.  Device-resident input and output, raw
+    library calls (the Python byte helpers would copy 4 GiB several times)."""
+    import ctypes as C
+    import torch
+    n = (4 << 30) + 5 * MIB
+    tile = 64 * MIB
+    piece = torch.frombuffer(bytearray(corpus.fill(1, tile, offset=12345)), dtype=torch.uint8).cuda()
+    dev_in = torch.empty(n, dtype=torch.uint8, device="cuda")
+    for off in range(0, n, tile):
+        k = min(tile, n - off)
+        dev_in[off:off + k].copy_(piece[:k])
+    torch.cuda.synchronize()                # the library works on its own streams
+    want_crc = jd.lib.zstrm_crc32update(0xFFFFFFFF, dev_in.data_ptr(), n) ^ 0xFFFFFFFF
+    tile_b = piece.cpu().numpy().tobytes()
+    crc = 0
+    for off in range(0, n, tile):
+        crc = zlib.crc32(tile_b[:min(tile, n - off)], crc)
+    assert crc == want_crc
+    out = bytearray()
+
+    def sink(buf, size, user):
+        out.extend(C.string_at(buf, size))
+        return size
+    ocb = api.OFN(sink)
+    z = jd.lib.zstrm_create(api.ZSTRM_DEFLATE | api.ZSTRM_GZIP, 1, None)
+    assert z
+    try:
+        jd.lib.zstrm_settargetfn(z, ocb, None)
+        step = 1 << 30
+        for off in range(0, n, step):
+            k = min(step, n - off)
+            assert jd.lib.zstrm_deflate(z, dev_in.data_ptr() + off, k) == k
+        jd.lib.zstrm_flush(z, 1)
+        assert z.contents.error == 0 and z.contents.total == n and z.contents.crc == want_crc
+    finally:
+        jd.lib.zstrm_destroy(z)
+    comp = bytes(out)
+    del out
+    assert comp[-8:-4] == want_crc.to_bytes(4, "little")
+    assert comp[-4:] == (n & 0xFFFFFFFF).to_bytes(4, "little") == (5 * MIB).to_bytes(4, "little")
+    # zlib reads it (streaming: sizes and CRC only)
+    dz = zlib.decompressobj(31)
+    total, crc = 0, 0
+    for off in range(0, len(comp), 16 * MIB):
+        b = dz.decompress(comp[off:off + 16 * MIB])
+        total += len(b)
+        crc = zlib.crc32(b, crc)
+    assert dz.eof and (total, crc) == (n, want_crc)
+    # and so does this library: memory source, 1 GiB reads into device memory
+    back = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+    zi = jd.lib.zstrm_create(api.ZSTRM_INFLATE | api.ZSTRM_GZIP, 0, None)
+    assert zi
+    try:
+        src = C.create_string_buffer(comp, len(comp))
+        jd.lib.zstrm_setsource(zi, C.cast(src, C.c_void_p).value, len(comp))
+        total = 0
+        while zi.contents.state != 4:
+            got = jd.lib.zstrm_inflate(zi, back.data_ptr(), 1 << 30)
+            if got <= 0:
+                break
+            assert torch.equal(back[:got], dev_in[total:total + got])
+            total += got
+        assert (zi.contents.error, total, zi.contents.total, zi.contents.crc) == (0, n, n, want_crc)
+        assert zi.contents.usedinput == len(comp)
+    finally:
+        jd.lib.zstrm_destroy(zi)

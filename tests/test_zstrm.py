@@ -240,3 +240,68 @@ def test_zlib_preset_dictionary_deflate(lib, corpus):
         assert got == d and zi.error == 0
     finally:
         zi.close()
+
+
+# ---- gzip files of several members (RFC 1952 2.2); the reference reads one, src/zstrm.c:626-667 ----
+
+def _members():
+    import base64
+    import json
+    from pathlib import Path
+    g = json.loads((Path(__file__).parent / "golden" / "gzip_members.json").read_text())
+    return {k: dict(v, gz=base64.b64decode(v["gz"])) for k, v in g.items()}
+
+
+@pytest.mark.parametrize("kw", [{}, {"via_callback": 100}, {"read": 1 << 20}, {"read": 1 << 20, "via_callback": 1 << 20},
+                                {"read": 1, "via_callback": 1}])
+def test_multi_member_gzip_fixtures(lib, kw):
+    """DESIGN.md deviation 11: every member is decoded (as gzip(1) and zlib's gzread do), each
+    with its own CRC-32 and ISIZE; bytes after the last member that are not a member are ignored."""
+    for name, c in _members().items():
+        if kw.get("read") == 1 and name != "five_members":
+            continue
+        got, err, (stype, crc, adler, total, used) = decompress(lib, c["gz"], **kw)
+        if c["size"] is not None:
+            assert err == 0, (name, err)
+            assert (len(got), zlib.crc32(got), total) == (c["size"], c["crc32"], c["size"]), name
+            assert stype == api.ZSTRM_GZIP
+        else:
+            # the broken second member: the first one arrives, then the error
+            assert err in (api.ZSTRM_EBADDATA, api.ZSTRM_ECHECKSUM, api.ZSTRM_ESRCEXHSTD, api.ZSTRM_EDEFLATE), (name, err)
+            assert got[:c["first_member_size"]] == got[:c["first_member_size"]] and zlib.crc32(got[:c["first_member_size"]]) == c["first_member_crc32"]
+
+
+def test_multi_member_of_our_own_members(lib, corpus):
+    parts = [corpus.fill(0, 70000, offset=1), b"", corpus.fill(2, 300000, offset=9), corpus.fill(1, 1000, offset=0)]
+    gz = b"".join(compress(lib, p, api.ZSTRM_GZIP, level=lv)[0] for p, lv in zip(parts, (6, 6, 1, 9)))
+    assert gzip.decompress(gz) == b"".join(parts)
+    for kw in ({}, {"via_callback": 4096}, {"read": 1 << 20, "via_callback": 1 << 20}):
+        got, err, (stype, crc, adler, total, used) = decompress(lib, gz, **kw)
+        assert err == 0 and got == b"".join(parts) and total == len(got) and used == len(gz)
+        assert crc == zlib.crc32(parts[-1])          # the running CRC-32 is the last member's
+
+
+def test_many_small_members(lib, corpus):
+    """bgzf-shaped input: hundreds of small members in one file."""
+    parts = [corpus.json_record(i)[:3000] for i in range(300)]
+    gz = b"".join(gzip.compress(p, 6, mtime=0) for p in parts)
+    got, err, info = decompress(lib, gz, read=1 << 20, via_callback=1 << 16)
+    assert err == 0 and got == b"".join(parts)
+
+
+def test_read_ahead_streaming_of_a_chunked_stream(lib):
+    """BASELINE configs[4] shape: our own gzip stream (independent chunks) read back through an
+    8 MiB source callback.  The inflator gathers several source windows per chunk-parallel step, the
+    queue grows while it holds bytes, and the trailer -- queued with an earlier window -- comes back
+    to zstrm at the end of the stream."""
+    import numpy as np
+    n = 40 << 20
+    data = np.random.RandomState(7).randint(0, 256, n, dtype=np.uint8).tobytes()
+    comp, _ = compress(lib, data, api.ZSTRM_GZIP, level=0, piece=8 << 20)
+    for piece in (8 << 20, 3 << 20):
+        got, err, (stype, crc, adler, total, used) = decompress(lib, comp, read=8 << 20, via_callback=piece)
+        assert err == 0 and total == n and used == len(comp)
+        assert crc == zlib.crc32(data) and zlib.crc32(got) == crc
+    # two such members in a row: what the first member's inflator had queued of the second comes back
+    got, err, (stype, crc, adler, total, used) = decompress(lib, comp + comp, read=8 << 20, via_callback=8 << 20)
+    assert err == 0 and total == 2 * n and used == 2 * len(comp) and zlib.crc32(got) == zlib.crc32(data + data)
