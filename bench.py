@@ -267,6 +267,41 @@ def verify_sharded(jd, api, torch, np, dist, rank, world, dev_in, dev_out, produ
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(torch, local):
+    """One process per GPU: run on (and allocate the page-locked host buffers from) the NUMA node
+    the GPU hangs off -- with every rank on node 0 the host staging traffic of the GPUs of the other
+    socket crosses the inter-socket link twice.  Best effort (containers may pin the CPU set); returns
+    what was done for the JSON line."""
+    import ctypes
+    out = {"node": None, "cpus": None, "mempolicy": None}
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return out
+        out["node"] = node
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+            out["cpus"] = len(use)
+        # memory of this process (cudaHostAlloc included) preferably from that node: MPOL_PREFERRED = 1
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))     # __NR_set_mempolicy on x86-64
+        out["mempolicy"] = "preferred" if rc == 0 else "errno %d" % ctypes.get_errno()
+    except Exception as ex:                                                     # reported, never required
+        out["note"] = repr(ex)
+    return out
+
+
 def _claim_stdout():
     """Everything any library prints to fd 1 during the run (NCCL's version banner, for one) goes
     to stderr; the returned file object is the real stdout, used once for the JSON line."""
@@ -317,6 +352,7 @@ def _main(real_stdout):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -578,7 +614,7 @@ def _main(real_stdout):
             "config": workload_config(args, {"chunk_kib": chunk_bytes >> 10,
                                              "collective": "all_gather of 24 B per rank, every step" if world > 1 else "none",
                                              "sharding": "one gzip member over %d ranks: DEFLT_FLUSH on all but the last" % world if world > 1 else "none"}),
-            "ratio": round(n / raw_produced, 4), "compressed_bytes_per_gpu": produced, "sharded": sharded,
+            "ratio": round(n / raw_produced, 4), "compressed_bytes_per_gpu": produced, "sharded": sharded, "numa": numa,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "inflate": inflate, "c4": c4, "c5": c5, "checksum": checksum,
             "gpu_launches": launches, "clocks": clocks,
         }

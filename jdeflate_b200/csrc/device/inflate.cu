@@ -769,10 +769,41 @@ inflate_stream(WarpMem* m, Stream& s)
 			if (!s.count_only) {
 				/* straight to the target, and into the ring for the matches of later blocks */
 				flush_ring(s, s.out, true);
-				for (uint64_t j = lane; j < n; j += 32) {
-					const uint8_t v = s.src[pos + j];
-					s.dst[s.out + j] = v;
-					s.ring[ring_index(s, (uint32_t) (s.out + j))] = v;
+				{
+					/* target-aligned 32-bit words, each from the two aligned source words that
+					 * hold its bytes; the head and tail bytes on their own.  Only the newest
+					 * RING bytes are worth a place in the ring. */
+					uint8_t* const d = s.dst + s.out;
+					const uint8_t* const p = s.src + pos;
+					uint64_t head = (uint64_t) ((4u - ((uintptr_t) d & 3u)) & 3u);
+					if (head > n) head = n;
+					const uint64_t nw = (n - head) >> 2;
+					const uint64_t tail0 = head + 4u * nw;
+					const uint64_t keep0 = n > RING ? n - RING : 0;      /* bytes from here on go to the ring */
+					if (lane < head) {
+						const uint8_t v = p[lane];
+						d[lane] = v;
+						if (lane >= keep0) s.ring[ring_index(s, (uint32_t) (s.out + lane))] = v;
+					}
+					const uint8_t* const ps = p + head;
+					const uint32_t* const pw = (const uint32_t*) ((uintptr_t) ps & ~(uintptr_t) 3);
+					const uint32_t sh = 8u * (uint32_t) ((uintptr_t) ps & 3u);
+					uint32_t* const dw = (uint32_t*) (d + head);
+					for (uint64_t i = lane; i < nw; i += 32) {
+						const uint32_t lo = __ldg(pw + i);
+						const uint32_t hi = sh ? __ldg(pw + i + 1) : 0u;      /* never past the word of the last byte */
+						const uint32_t v = __funnelshift_r(lo, hi, sh);
+						dw[i] = v;
+						if (head + 4u * i + 4u > keep0)      /* (a word that straddles keep0 brings up to 3 older bytes:
+						                                      * their slots are rewritten by this lane, or by the tail below) */
+							*(uint32_t*) (s.ring + ((uint32_t) (uintptr_t) (dw + i) & (RING - 1u))) = v;
+					}
+					__syncwarp();
+					if (tail0 + lane < n) {
+						const uint8_t v = p[tail0 + lane];
+						d[tail0 + lane] = v;
+						s.ring[ring_index(s, (uint32_t) (s.out + tail0 + lane))] = v;
+					}
 				}
 				s.flushed = s.out + n;
 				const int64_t lo = (int64_t) (s.out + n) - (int64_t) RING;
