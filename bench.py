@@ -183,7 +183,8 @@ def run_reference_arm(args, real_stdout=sys.stdout):
         "impl": "reference", "metric": "deflate_level%d_GBps_uncompressed" % args.level, "value": round(value, 4),
         "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(args, extra={"note": "CPU reference: each step is a bounded sample of the workload"}),
+        "config": workload_config(args),
+        "note": "CPU reference: each step is a bounded sample of the workload",
         "cpu_baseline": {"value": round(value, 4), "unit": "GB/s", "cores": cores, "kind": kind,
                          "sample": f"{sample // MIB} MiB of the mixed corpus, one reference TDeflator per core on contiguous slices"},
         "e2e": {"value": round(value, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -611,9 +612,10 @@ def _main(real_stdout):
             "metric": "deflate_level%d_GBps_uncompressed" % args.level, "value": round(value, 3), "unit": "GB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args, {"chunk_kib": chunk_bytes >> 10,
-                                             "collective": "all_gather of 24 B per rank, every step" if world > 1 else "none",
-                                             "sharding": "one gzip member over %d ranks: DEFLT_FLUSH on all but the last" % world if world > 1 else "none"}),
+            "config": workload_config(args),
+            "implementation": {"chunk_kib": chunk_bytes >> 10,
+                               "collective": "all_gather of 24 B per rank, every step" if world > 1 else "none",
+                               "sharding": "one gzip member over %d ranks: DEFLT_FLUSH on all but the last" % world if world > 1 else "none"},
             "ratio": round(n / raw_produced, 4), "compressed_bytes_per_gpu": produced, "sharded": sharded, "numa": numa,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "inflate": inflate, "c4": c4, "c5": c5, "checksum": checksum,
             "gpu_launches": launches, "clocks": clocks,
