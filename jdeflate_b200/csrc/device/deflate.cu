@@ -45,7 +45,8 @@ struct WorkLayout {
 static int plan(uint64_t n, const jdb_deflate_cfg* cfg, WorkLayout* L)
 {
 	/* a CTA of the LZ kernel takes two consecutive segments of one chunk */
-	if (cfg->chunk_bytes == 0 || cfg->chunk_bytes % (2 * SEG) || cfg->block_segs == 0 || cfg->block_segs > 16) return JDB_EARG;
+	/* chunks are whole pairs of segments (an lz_kernel CTA), or exactly one segment */
+	if (cfg->chunk_bytes == 0 || (cfg->chunk_bytes % (2 * SEG) && cfg->chunk_bytes != SEG) || cfg->block_segs == 0 || cfg->block_segs > 16) return JDB_EARG;
 	if (cfg->chunk_len && (n % cfg->chunk_bytes || cfg->dict_region || cfg->chunk_bytes > CHUNK_LEN_MASK)) return JDB_EARG;
 	const uint64_t nseg = (n + SEG - 1) / SEG;
 	const uint64_t nchunks = n ? (n + cfg->chunk_bytes - 1) / cfg->chunk_bytes : 1;

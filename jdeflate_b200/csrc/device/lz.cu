@@ -551,19 +551,31 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 	const uint32_t lane = tid & 31u;
 	LzGroup& S = W.g[grp];
 
-	/* the pair of segments of this CTA (same chunk: chunk sizes are multiples of both) */
+	/* the pair of segments of this CTA.  Chunk sizes are multiples of the pair -- both segments lie
+	 * in one chunk and share its history -- or exactly one segment (small records, one per slot:
+	 * jdb200_deflate_batch): then the pair is two chunks, each group has its own, and all they share
+	 * is the staged window. */
 	const uint64_t pair0 = (uint64_t) blockIdx.x * (LZ_GROUPS * SEG);
-	const uint64_t chunk0 = pair0 / chunk_bytes * chunk_bytes;
-	const uint64_t chunk1 = chunk_end(chunk_len, chunk0, chunk_bytes, n);
-	if (pair0 >= chunk1) return;                 /* ragged chunk: empty segment slots (the whole CTA leaves) */
+	const bool split = chunk_bytes < LZ_GROUPS * SEG;
+	const uint64_t chunkA0 = pair0 / chunk_bytes * chunk_bytes;
+	const uint64_t chunkA1 = chunk_end(chunk_len, chunkA0, chunk_bytes, n);
+	uint64_t chunkB0 = chunkA0, chunkB1 = chunkA1;
+	if (split && pair0 + SEG < n) {
+		chunkB0 = pair0 + SEG;
+		chunkB1 = chunk_end(chunk_len, chunkB0, chunk_bytes, n);
+	}
+	/* the end of the data this CTA looks at */
 	uint64_t pair1 = pair0 + LZ_GROUPS * SEG;
-	if (pair1 > chunk1) pair1 = chunk1;
-	const uint64_t hist0 = pair0 >= chunk0 + WND ? pair0 - WND : chunk0;  /* first staged byte */
+	if (!split) { if (pair1 > chunkA1) pair1 = chunkA1; }
+	else pair1 = chunkB1 > chunkB0 ? chunkB1 : chunkA1;
+	if (pair0 >= pair1) return;                  /* ragged chunk(s): empty segment slots (the whole CTA leaves) */
+	const uint64_t hist0 = pair0 >= chunkA0 + WND ? pair0 - WND : chunkA0;  /* first staged byte */
+	const uint64_t stage1 = split ? pair1 : chunkA1;                        /* staged bytes end here at the latest */
 	LZ_PROF_INIT();
 
 	/* ---- stage bytes and links (16-byte vectors; `in` and hist0 are 16-aligned) ---- */
 	if (blockIdx.x * LZ_GROUPS + LZ_GROUPS > prm.skip_segs) {
-		const uint32_t nbytes = (uint32_t) ((chunk1 - hist0) < (uint64_t) DATA_BYTES ? (chunk1 - hist0) : DATA_BYTES);
+		const uint32_t nbytes = (uint32_t) ((stage1 - hist0) < (uint64_t) DATA_BYTES ? (stage1 - hist0) : DATA_BYTES);
 		const uint4* src = (const uint4*) (in + hist0);
 		uint4* dst = (uint4*) W.data;
 		const uint32_t nv = nbytes / 16;
@@ -605,6 +617,8 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 	const uint32_t seg = blockIdx.x * LZ_GROUPS + grp;
 	if (seg < prm.skip_segs) return;             /* dictionary: nothing to parse, nothing to emit */
 	const uint64_t seg0 = (uint64_t) seg * SEG;
+	const uint64_t chunk0 = grp ? chunkB0 : chunkA0;                      /* the chunk of this group's segment */
+	const uint64_t chunk1 = grp ? chunkB1 : chunkA1;
 	if (seg0 >= chunk1) return;                  /* ragged chunk: empty segment slot */
 	uint64_t seg1 = seg0 + SEG;
 	if (seg1 > chunk1) seg1 = chunk1;
@@ -612,8 +626,10 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 	const uint32_t nwords = (seg_len + 31) / 32;                          /* bitmap words in use */
 	const uint32_t hoff = (uint32_t) (seg0 - hist0);                      /* segment start in smem coords */
 
-	/* with a preset dictionary the padding in front of it is not history */
-	const uint32_t first_valid = (chunk0 == 0 && prm.hist_min > hist0) ? (uint32_t) (prm.hist_min - hist0) : 0u;
+	/* what lies in front of this group's chunk in the staged window is not its history: the
+	 * padding in front of a preset dictionary, the other group's chunk */
+	uint32_t first_valid = (chunk0 == 0 && prm.hist_min > hist0) ? (uint32_t) (prm.hist_min - hist0) : 0u;
+	if (chunk0 > hist0 && (uint32_t) (chunk0 - hist0) > first_valid) first_valid = (uint32_t) (chunk0 - hist0);
 
 	/* ---- pass 1: the first chain candidate of every position -----------------
 	 * One link, one comparison per position, converged.  It seeds the search
@@ -943,7 +959,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 		lz_gsync(grp);
 	}
 	if (prm.short3 && (prm.short3 > 1 || (S.nomatch * 5u > seg_len * 2u && S.nomatch * 20u < seg_len * 19u))) {
-		const uint32_t sv = (chunk0 == 0 && prm.hist_min > hist0) ? (uint32_t) (prm.hist_min - hist0) : 0u;   /* 40 % .. 95 %: not random data either */
+		const uint32_t sv = first_valid;             /* 40 % .. 95 %: not random data either */
 		for (uint32_t k = 0; k < PER_THREAD; k++) {
 			const uint32_t p = tid + k * LZ_GTHREADS;
 			if (p + 3 > seg_len || S.m[p] != 0) continue;

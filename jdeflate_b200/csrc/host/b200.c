@@ -199,12 +199,15 @@ jdb200_deflate_batch(const uint8* source, uint8* target,
 	}
 	/* chunk slot: twice the mean record, a power of two between one LZ segment and the
 	 * chunk size of the streaming encoder (longer records span several chunks) */
-	chunk = 2 * JDB_SEG;
+	chunk = JDB_SEG;        /* one segment: an lz_kernel CTA then works on two records at a time */
 	while (chunk < DB_MAX_CHUNK && chunk < 2 * (totalbytes / count)) chunk *= 2;
 	{
 		const char* e = getenv("JDB200_RECORD_CHUNK_KIB");
-		if (e && atoi(e) > 0) chunk = ((size_t) atoi(e) << 10) / (2 * JDB_SEG) * (2 * JDB_SEG);
-		if (chunk < 2 * JDB_SEG) chunk = 2 * JDB_SEG;
+		if (e && atoi(e) > 0) {
+			chunk = (size_t) atoi(e) << 10;
+			if (chunk > JDB_SEG) chunk = chunk / (2 * JDB_SEG) * (2 * JDB_SEG);
+		}
+		if (chunk < JDB_SEG) chunk = JDB_SEG;
 	}
 	budget = DB_GROUP_BYTES;
 	{

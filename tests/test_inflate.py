@@ -237,3 +237,89 @@ def test_parallel_path_small_source_windows(lib, corpus, monkeypatch):
         st, err, out, used = lib.inflate_bytes(z, len(d), feed=feed, final=False)
         assert (st, err, used) == (api.OK, 0, len(z)), feed
         assert out == d, feed
+
+
+# ---- the lane-parallel rounds, the output ring and the word copies (round 2) ----------------------
+
+def test_lane_parallel_rounds_shapes(lib, oracle):
+    """Inputs that push the lane-parallel symbol decode to its edges: one- and two-bit codes (a lane's
+    token slots run out long before its subsequence ends), maximal matches, literal-only blocks with the
+    fixed code, a long run (distance 1, overlapping copies), blocks that end inside a round."""
+    import numpy as np
+    rs = np.random.RandomState(3)
+    cases = {
+        "zeros": bytes(300000),
+        "two_symbols": bytes(rs.randint(0, 2, 200000, dtype=np.uint8) * 65),
+        "four_symbols": bytes(rs.randint(0, 4, 200000, dtype=np.uint8) + 97),
+        "random_literals": rs.randint(0, 256, 150000, dtype=np.uint8).tobytes(),
+        "period_258": (bytes(range(256)) + b"ab") * 600,
+        "long_run_then_noise": b"\x07" * 70000 + rs.randint(0, 256, 3000, dtype=np.uint8).tobytes() + b"\x07" * 70000,
+    }
+    for name, d in cases.items():
+        for lvl, strategy in ((6, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (9, zlib.Z_RLE)):
+            c = zlib.compressobj(lvl, zlib.DEFLATED, -15, 9, strategy)
+            z = c.compress(d) + c.flush()
+            st, err, out, used = lib.inflate_bytes(z, len(d) + 1)
+            assert (st, err, used) == (api.OK, 0, len(z)), (name, lvl, strategy)
+            assert out == d, (name, lvl, strategy)
+    # many short blocks: Z_FULL_FLUSH every few hundred bytes puts block ends (and stored markers) inside rounds
+    d = cases["four_symbols"][:60000]
+    c = zlib.compressobj(6, zlib.DEFLATED, -15)
+    z = b"".join(c.compress(d[i:i + 700]) + c.flush(zlib.Z_FULL_FLUSH) for i in range(0, len(d), 700)) + c.flush()
+    st, err, out, used = lib.inflate_bytes(z, len(d))
+    assert (st, err, used) == (api.OK, 0, len(z)) and out == d
+
+
+def test_target_windows_cut_lane_parallel_rounds(lib, corpus):
+    """The target room ends inside a round: the chain is cut, the step-by-step decoder finishes the window,
+    a match cut by the window end is continued by the next call."""
+    d = corpus.fill(4, 40000, offset=11) + bytes(5000) + corpus.fill(0, 20000, offset=3)
+    z = zlib_raw(d, 6)
+    for window in (1, 2, 3, 5, 17, 255, 258, 259, 1000, 4095, 4096, 4097, 33000):
+        st, err, out, used = lib.inflate_bytes(z, len(d), window=window)
+        assert (st, err, used) == (api.OK, 0, len(z)), window
+        assert out == d, window
+    # exact fit, one byte short, and a target that ends inside a long match
+    for cap in (len(d), len(d) - 1, 40000 + 2500):
+        st, err, out, used = lib.inflate_bytes(z, cap)
+        assert st == (api.OK if cap == len(d) else api.TGTEXHSTD) and out == d[:cap], cap
+
+
+def test_far_offset_inside_a_round_matches_oracle(lib, oracle):
+    """A distance that reaches beyond the bytes produced so far, deep inside the input (not at its start): the
+    round drops the lane that holds it and the step-by-step decoder reports the reference's error and output."""
+    from support import BitWriter
+    for lits in (40, 300, 2000):
+        w = BitWriter()
+        w.put(1, 1); w.put(1, 2)                        # final, fixed code
+        def lit(b):
+            if b < 144: w.huff(0x30 + b, 8)
+            else: w.huff(0x190 + b - 144, 9)
+        for i in range(lits):
+            lit((i * 7) & 0x7f)
+        # length 3 (symbol 257, 7 bits 0000001), distance code 29 + 13 extra bits all ones = 32768
+        w.huff(1, 7); w.huff(29, 5); w.put(0x1fff, 13)
+        for i in range(64):
+            lit(65)
+        w.huff(0, 7)                                    # end of block
+        z = w.bytes()
+        got = lib.inflate_bytes(z, lits + 200)
+        want = oracle.inflate(z, lits + 200)
+        assert got[:2] == (want[0], want[1]) == (api.ERROR, api.INFLT_EFAROFFSET), lits
+        assert got[2] == want[2] and len(got[2]) == lits
+
+
+def test_batch_records_at_every_alignment(lib, corpus):
+    """Output ring words line up with target words: records whose target offsets and lengths hit every
+    alignment, stored and compressed, through the batch call."""
+    import numpy as np
+    rs = np.random.RandomState(5)
+    recs, streams = [], []
+    for i in range(48):
+        n = 1 + (i * 37) % 300 + (i % 5) * 1000
+        r = corpus.fill(i % 5, n, offset=i * 1000) if i % 3 else rs.randint(0, 256, n, dtype=np.uint8).tobytes()
+        recs.append(r)
+        streams.append(zlib_raw(r, 0 if i % 4 == 0 else 6))
+    outs, res = lib.inflate_batch_bytes(streams, [len(r) for r in recs], fmt=api.JDB200_RAW)
+    for i, (r, o, q) in enumerate(zip(recs, outs, res)):
+        assert (q.status, q.error) == (api.OK, 0) and o == r, i
