@@ -570,7 +570,14 @@ emit_queue(Stream& s, uint32_t* pend, const uint32_t* queue, uint32_t nq, uint32
 		/* short match from older bytes */
 		if (src >= s.ring_lo) {
 			const uint32_t ri = ring_index(s, (uint32_t) src);
-			for (uint32_t j = 0; j < emit; j++) s.ring[(wi + j) & (RING - 1u)] = s.ring[(ri + j) & (RING - 1u)];
+			if (wi + emit <= RING && ri + emit <= RING) {
+				/* neither range wraps around the ring (nearly always): plain pointers */
+				const uint8_t* const rp = s.ring + ri;
+				uint8_t* const wp = s.ring + wi;
+				for (uint32_t j = 0; j < emit; j++) wp[j] = rp[j];
+			} else {
+				for (uint32_t j = 0; j < emit; j++) s.ring[(wi + j) & (RING - 1u)] = s.ring[(ri + j) & (RING - 1u)];
+			}
 		} else if (src >= 0 && src + (int64_t) emit <= s.ring_lo) {
 			/* all of it in L2: the (up to five) aligned words that hold the source bytes are
 			 * loaded together -- one round trip instead of one per byte */

@@ -25,7 +25,8 @@ for r in rows[hi + 1:]:
     ln = addr2line.get(a - base)
     agg[ln] += int(r[ci] or 0); aggi[ln] += int(r[ie] or 0); aggt[ln] += int(r[it] or 0)
 ts = sum(agg.values()); ti = sum(aggi.values())
-src = open('/root/repo/jdeflate_b200/csrc/device/' + srcfile).read().split('\n')
+import os
+src = open(os.environ.get('NCU_SRC') or '/root/repo/jdeflate_b200/csrc/device/' + srcfile).read().split('\n')   # NCU_SRC: the source as it was when the capture was taken
 print("total warp-instructions %d, samples %d" % (ti, ts))
 for ln in sorted(aggi, key=lambda x: (str(x[0]), x[1]) if x else ("", 0)):
     c = aggi[ln]
