@@ -258,3 +258,20 @@ def test_batch_api_records(lib, oracle, corpus, monkeypatch):
     assert lib.lib.jdb200_deflate_batch(None, None, None, None, 3, api.JDB200_RAW, 6) != 0
     assert lib.lib.jdb200_deflate_batch(b"x", b"y", b"z" * 32, b"w" * 32, 1, api.JDB200_RAW, 10) != 0
     assert lib.lib.jdb200_deflate_batch(None, None, None, None, 0, api.JDB200_RAW, 6) == 0
+
+
+def test_sparse_matches_in_record_structured_data(lib, oracle):
+    """lz_kernel samples one position in 16 to tell segments with nothing to find (emitted as literals at
+    once) from the rest.  Records of 16 bytes whose only repeating field sits at a fixed offset must not
+    alias with that sample: 12 random bytes + a 4-byte field that repeats from record to record."""
+    import numpy as np
+    rs = np.random.RandomState(11)
+    for field_at in (0, 5, 12):
+        rec = rs.randint(0, 256, (8192, 16), dtype=np.uint8)
+        rec[:, field_at:field_at + 4] = np.frombuffer(b"\xde\xad\xbe\xef", np.uint8)
+        d = rec.tobytes()
+        z = lib.deflate_bytes(d, 6)
+        check_stream(oracle, z, d)
+        ref = len(oracle.deflate(d, 6))
+        assert ref < 0.97 * len(d)                       # the field is worth compressing
+        assert len(z) <= RATIO_TOLERANCE * ref + 16, (field_at, len(z), ref)
