@@ -29,6 +29,7 @@
 /* chunk-parallel decode of one stream (streams cut by sync markers, i.e. ours) */
 #define PAR_MAXC      65536u                  /* marker candidates per step    */
 #define PAR_MIN_BYTES ((size_t) 4 << 20)      /* queued input that makes a step worthwhile */
+#define PAR_FIRST_BYTES ((size_t) 32 << 20)   /* ... for the first step of a caller that reads ahead (zstrm) */
 #define PAR_MAXFRAG   4096u                   /* chunks decoded per step (slots of par_stride bytes each) */
 #define PAR_STRIDE    ((size_t) 1 << 20)      /* first guess of the slot size: the encoder's largest default chunk */
 #define PAR_STRIDE_MAX ((size_t) 16 << 20)
@@ -269,6 +270,9 @@ void
 jdb_inflator_set_readahead(TInflator* state, size_t bytes)
 {
 	PRVT->readahead = bytes;
+	if (bytes && PRVT->par_total == 0) {
+		PRVT->par_want = bytes < PAR_FIRST_BYTES ? bytes : PAR_FIRST_BYTES;
+	}
 }
 
 /* zstrm: the memory of the last source window is gone (its read buffer was reused): nothing
@@ -775,7 +779,9 @@ inflator_inflate(TInflator* state, uint32 final)
 		/* a stream cut into chunks by sync markers (ours) is decoded chunk-parallel
 		 * while the decoder sits at a block boundary */
 		if (PRVT->par_ok) {
-			const int chain = PRVT->readahead && PRVT->par_total != 0 && PRVT->par_starved;
+			/* with read-ahead (zstrm) the first step, too, waits for a good deal of input: a step
+			 * costs the time of its slowest chunk however few chunks it holds */
+			const int chain = PRVT->readahead && (PRVT->par_total == 0 || PRVT->par_starved);
 			int step = PRVT->inqlen >= (chain ? PRVT->par_want : PAR_MIN_BYTES) ||
 			           (PBLC->finalinput && absorbed_all && PRVT->inqlen >= ((size_t) 256 << 10));
 			if (!step && chain && !PBLC->finalinput) {

@@ -654,7 +654,14 @@ inflate(struct TZStrmPrvt* zstrm, uint8* buffer, uintxx total)
 			return (uintxx) (buffer - bbgn);
 		}
 		if (zstrm->result == INFLT_ERROR) {
-			fail(zstrm, ZSTRM_EDEFLATE);
+			/* a stream that is longer than the input is the source's fault (the reference: the
+			 * callback has nothing more to give, src/zstrm.c:842-858), anything else the data's */
+			if (zstrm->srceof && infltr->error == INFLT_EINPUTEND) {
+				fail(zstrm, zstrm->iofn ? ZSTRM_EBADDATA : ZSTRM_ESRCEXHSTD);
+			}
+			else {
+				fail(zstrm, ZSTRM_EDEFLATE);
+			}
 			break;
 		}
 		if (zstrm->result == INFLT_SRCEXHSTD || zstrm->srcset == 0) {

@@ -32,7 +32,7 @@ class ShardPlan:
     last: bool          # this rank closes the stream (DEFLT_END), the others DEFLT_FLUSH
 
 
-def plan(total_bytes: int, world: int, rank: int, chunk_bytes: int = 256 << 10) -> ShardPlan:
+def plan(total_bytes: int, world: int, rank: int, chunk_bytes: int = 512 << 10) -> ShardPlan:
     """Contiguous, chunk aligned slice of rank `rank` (reference-independent: SURVEY 8e)."""
     if world < 1 or not 0 <= rank < world:
         raise ValueError("bad rank / world")
