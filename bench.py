@@ -155,10 +155,11 @@ def cpu_reference(corpus, op, level, sample_bytes, threads, offset=0):
 
 
 def cpu_sample_size(cores, total):
-    # >= 2 s of wall time: 60 MiB of the mixed corpus per core (whole TEXT/BINARY/INCOMP cycles of
-    # 12 MiB); the sample may be larger than one GPU step's input -- it is a sample of the same
-    # corpus, and a longer one is a steadier denominator
-    n = 60 * MIB * max(1, cores)
+    # >= 2 s of wall time: 120 MiB of the mixed corpus per core (whole TEXT/BINARY/INCOMP cycles of
+    # 12 MiB; the reference does 50-55 MB/s per core at level 6: 60 MiB per core came to 1.1-1.6 s); the
+    # sample may be larger than one GPU step's input -- it is a sample of the same corpus, and a
+    # longer one is a steadier denominator
+    n = 120 * MIB * max(1, cores)
     return max(12 * MIB, n - n % (12 * MIB))
 
 
