@@ -275,3 +275,30 @@ def test_sparse_matches_in_record_structured_data(lib, oracle):
         ref = len(oracle.deflate(d, 6))
         assert ref < 0.97 * len(d)                       # the field is worth compressing
         assert len(z) <= RATIO_TOLERANCE * ref + 16, (field_at, len(z), ref)
+
+
+def test_preset_dictionary_stream_larger_than_a_chunk_against_the_reference(lib, ref, corpus):
+    """DESIGN.md deviation 10: the dictionary is history for the first chunk only.  The reference's sliding window
+    carries it 32 KiB far, so on a stream of several chunks both encoders get the same benefit: the sizes stay within
+    the 3 % bar, and the reference's inflator (given the dictionary) reads our stream back."""
+    dct = corpus.fill(4, 30000, offset=1)
+    d = corpus.fill(4, 3 * 512 * 1024 + 12345, offset=9)
+    sizes = {}
+    for name, l in (("ours", lib), ("ref", ref)):
+        de = l.deflator(6)
+        try:
+            de.setdctnr(dct)
+            z = de.run(d)
+        finally:
+            de.close()
+        assert zlib.decompressobj(-15, zdict=dct).decompress(z) == d, name
+        sizes[name] = len(z)
+        if name == "ours":
+            s = ref.inflator()
+            try:
+                s.setdctnr(dct)
+                st, err, out, used = s.run(z, len(d))
+                assert (st, err, used) == (api.OK, 0, len(z)) and out == d
+            finally:
+                s.close()
+    assert sizes["ours"] <= RATIO_TOLERANCE * sizes["ref"], sizes
