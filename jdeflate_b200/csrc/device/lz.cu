@@ -33,7 +33,7 @@
  *                 (good length, the reference's offset-aware accept rule
  *                 src/deflator.c:2860-2879) is evaluated per position, and the
  *                 one truly serial step -- following the chosen tokens from
- *                 the segment start -- is done by 64 speculative walkers
+ *                 the segment start -- is done by 128 speculative walkers
  *                 whose paths are stitched exactly (paths re-converge within a
  *                 few tokens).  Tokens are compacted with a block scan and
  *                 written coalesced; symbol histograms are accumulated with
@@ -245,9 +245,11 @@ chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, u
 #define LZ_WALK_STEPS 2
 #endif
 #define PER_THREAD   (SEG / LZ_GTHREADS)           /* 16 */
-#define WALK_BLOCK   128u
-#define WALKERS      (SEG / WALK_BLOCK)            /* 64 */
-#define WORDS_PER_WB (WALK_BLOCK / 32)             /* 4 */
+#ifndef WALK_BLOCK
+#define WALK_BLOCK   64u       /* 128: 2-3 % slower (the walkers are a serial step; round 2) */
+#endif
+#define WALKERS      (SEG / WALK_BLOCK)            /* 128 */
+#define WORDS_PER_WB (WALK_BLOCK / 32)             /* 2 */
 #define DATA_BYTES   (WND + LZ_GROUPS * SEG + 320) /* history + segments + look-ahead/guard */
 #define NOPOS        0xffffffffu
 
@@ -310,6 +312,7 @@ struct LzParams {
 	uint32_t succ;                   /* successors of path positions are searched as well (the lazy rule reads them) */
 	uint32_t prewalk;                /* links followed in pass 1 to tell how long a position's chain is (<= 8) */
 	uint32_t skip_div;               /* no search at all when fewer than 1/skip_div of the positions matched in pass 1 */
+	uint32_t r2min;                  /* no second round when the first improved fewer than 1/r2min of the positions (0: always two) */
 };
 
 struct LzGroup {
@@ -329,6 +332,8 @@ struct LzGroup {
 	uint32_t nomatch;                /* positions without a match (3-byte probe switch) */
 	uint32_t conflict;               /* first block whose speculative landing turned out wrong */
 	uint32_t nmatch1;                /* positions whose first candidate matched */
+	uint32_t improved;               /* positions whose match the last search round improved */
+	uint32_t pad_;                   /* sizeof(LzGroup) stays a multiple of 8: land[] is read as uint2 */
 	uint32_t ccount[2];              /* positions queued per class, 2 x 16 bits each */
 	uint32_t next_batch;
 };
@@ -341,6 +346,7 @@ struct LzSmem {
 	LzGroup  g[LZ_GROUPS];
 };
 
+static_assert(sizeof(LzGroup) % 8 == 0, "the second group's arrays are read with 8-byte vector loads");
 static_assert(sizeof(LzSmem) <= 232448, "LzSmem must fit the 227 KB of shared memory a CTA can have");
 
 /* barrier of one group (named barrier 1 + group) */
@@ -384,7 +390,7 @@ next_pos(const LzGroup& S, uint32_t p)
  * following the chosen tokens from the segment start, and paths that start at different
  * positions re-converge within a few tokens, so:
  *   (1) per position: would a parser arriving here take the match (lazy rule)?
- *   (2) one speculative walker per 128 positions follows the decisions from the start of
+ *   (2) one speculative walker per 64 positions follows the decisions from the start of
  *       its block until it leaves the block (land[]);
  *   (3) one thread chains the landings: the true path enters block w where the last
  *       entered block before it landed -- provided the path through that block joined
@@ -420,7 +426,7 @@ lz_parse_phase(LzGroup& S, const uint32_t grp, const LzParams& prm, const uint32
 	lz_gsync(grp);
 	LZ_PROF_MARK(LZP_PA);
 
-	/* ---- speculative walkers: one per 128 positions ---- */
+	/* ---- speculative walkers: one per 64 positions ---- */
 	if (tid < nblk) {
 		const uint32_t b0 = tid * WALK_BLOCK, b1 = b0 + WALK_BLOCK;
 		const uint32_t lim = b1 < seg_len ? b1 : seg_len;
@@ -794,7 +800,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 			S.need[tid] = nd;
 			S.done[tid] |= nd;
 		}
-		if (tid == 0) { S.ccount[0] = 0; S.ccount[1] = 0; S.next_batch = 0; }
+		if (tid == 0) { S.ccount[0] = 0; S.ccount[1] = 0; S.next_batch = 0; S.improved = 0; }
 	}
 	lz_gsync(grp);
 
@@ -898,7 +904,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 
 			/* set the search up; pass 1 already looked at the first candidate (and there
 			 * is a second one: class > 0) */
-			uint32_t p = 0, j = 0, jmin = 0, maxlen = 0, best = 0, bestd = 0, cur = 0, steps = 0, cb = 0;
+			uint32_t p = 0, j = 0, jmin = 0, maxlen = 0, best = 0, bestd = 0, cur = 0, steps = 0, cb = 0, first_len = 0;
 			uint32_t dmax = 0, jw0 = 0, jw1 = 0;
 			bool walking = false;
 			if (mine) {
@@ -912,6 +918,7 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 				const uint32_t v1 = S.m[p];
 				best = MINLEN - 1;
 				if (v1) { best = v1 >> 16; bestd = v1 & 0xffffu; }
+				first_len = best;
 				steps = (((S.fix[p >> 5] >> (p & 31u)) & 1u) ? prm.chain >> 1 : prm.chain) - 1;
 				cur = W.prev[j];
 				cb = W.data[j + best];
@@ -982,12 +989,18 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 				}
 			}
 			if (mine) S.m[p] = best >= MINLEN ? (best << 16) | bestd : 0;
+			if (prm.r2min) {
+				const unsigned im = __ballot_sync(JDB_FULL_MASK, mine && best >= MINLEN && best > first_len);
+				if (lane == 0 && im) atomicAdd(&S.improved, (uint32_t) __popc(im));
+			}
 		}
 #undef LZ_BATCH_ENTRY
 		LZ_PROF_FLUSH();
 	}
 	lz_gsync(grp);
 	LZ_PROF_MARK(LZP_SEARCH);
+	/* a round that improved next to nothing leaves the next parse where it was: no second round */
+	if (prm.r2min && S.improved * prm.r2min < seg_len) break;
 	}       /* rounds */
 
 	/* ---- 3-byte matches ------------------------------------------------------
@@ -1102,12 +1115,13 @@ extern "C" int jdb_lz_chain(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
 }
 
 /* experiment switches, read once per process (JDB_LZ_*; -1 = the level's default) */
-struct LzEnv { int rounds, short3, patience, tlazy, succ, prewalk, skip_div; };
+struct LzEnv { int rounds, short3, patience, tlazy, succ, prewalk, skip_div, r2min; };
 static int lz_env_int(const char* name) { const char* v = getenv(name); return v ? atoi(v) : -1; }
 static const LzEnv& lz_env()
 {
 	static const LzEnv e = { lz_env_int("JDB_LZ_ROUNDS"), lz_env_int("JDB_LZ_SHORT3"), lz_env_int("JDB_LZ_PATIENCE"),
-	                         lz_env_int("JDB_LZ_TLAZY"), lz_env_int("JDB_LZ_SUCC"), lz_env_int("JDB_LZ_PREWALK"), lz_env_int("JDB_LZ_SKIP_DIV") };
+	                         lz_env_int("JDB_LZ_TLAZY"), lz_env_int("JDB_LZ_SUCC"), lz_env_int("JDB_LZ_PREWALK"), lz_env_int("JDB_LZ_SKIP_DIV"),
+	                         lz_env_int("JDB_LZ_R2MIN") };
 	return e;
 }
 
@@ -1136,6 +1150,7 @@ extern "C" int jdb_lz_parse(const uint8_t* in, uint64_t n, uint32_t chunk_bytes,
 	if (prm.prewalk > 8) prm.prewalk = 8;
 	if (prm.prewalk + 1 > chain) prm.prewalk = chain ? chain - 1 : 0;
 	prm.skip_div = env.skip_div >= 0 ? (uint32_t) env.skip_div : 64u;
+	prm.r2min = env.r2min >= 0 ? (uint32_t) env.r2min : 0u;
 	const uint64_t npair = (n + LZ_GROUPS * SEG - 1) / (LZ_GROUPS * SEG);
 	JDB_LAUNCH(lz_kernel, dim3((unsigned) npair), dim3(LZ_THREADS), smem, s,
 	           in, n, chunk_bytes, chunk_len, prev, prm, tok, seg_ntok, seg_hist);
