@@ -640,14 +640,15 @@ struct LaneRun {
 };
 
 static __device__ LANE_INLINE void
-lane_decode(const WarpMem* m, uint32_t* slots, LaneRun& r, uint32_t start, uint32_t limit, uint32_t safe_end)
+lane_decode(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, uint32_t* slots, LaneRun& r,
+            uint32_t start, uint32_t limit, uint32_t safe_end)
 {
 	uint32_t pos = start, n = 0, bytes = 0, flag = PF_OK;
 	int32_t need = 0;
 	while (pos < limit) {
 		if (n >= PQ_K) { flag = PF_FULL; break; }
-		const uint32_t bits = peek32(m->inbuf, pos);
-		const uint32_t e = lookup32(m->lit, bits, LIT_ROOT);
+		const uint32_t bits = peek32(inbuf, pos);
+		const uint32_t e = lookup32(lit, bits, LIT_ROOT);
 		const uint32_t nb = e & 15u;
 		const uint32_t type = (e >> 8) & 3u;
 		uint32_t tok;
@@ -661,8 +662,8 @@ lane_decode(const WarpMem* m, uint32_t* slots, LaneRun& r, uint32_t start, uint3
 			const uint32_t lxb = (e >> 4) & 15u;
 			const uint32_t len = (e >> 16) + ((bits >> nb) & ((1u << lxb) - 1u));
 			const uint32_t o2 = pos + nb + lxb;
-			const uint32_t bits2 = peek32(m->inbuf, o2);
-			const uint32_t d = lookup32(m->dist, bits2, DIST_ROOT);
+			const uint32_t bits2 = peek32(inbuf, o2);
+			const uint32_t d = lookup32(dtab, bits2, DIST_ROOT);
 			const uint32_t dnb = d & 15u, dxb = (d >> 4) & 15u;
 			if (dnb == 0 || (d >> 16) == 0) { flag = PF_ANOM; break; }
 			const uint32_t dist = (d >> 16) + ((bits2 >> dnb) & ((1u << dxb) - 1u));
@@ -684,12 +685,311 @@ lane_decode(const WarpMem* m, uint32_t* slots, LaneRun& r, uint32_t start, uint3
 	r.start = start; r.end = pos; r.n = n; r.bytes = bytes; r.flag = flag; r.need = need;
 }
 
+/* ---- one stream on a whole CTA (inflate_wide_kernel) ---------------------------
+ *
+ * One warp per stream is the right shape for a batch of records; a caller with ONE stream
+ * that carries no chunk markers (anybody's zlib / gzip output through inflator_inflate)
+ * leaves a lone warp to the dependent latency of every instruction it issues.  The wide
+ * kernel gives such a stream a CTA of WIDE_WARPS warps.  Warp 0 (the master) runs
+ * inflate_stream as it is -- block headers, tables, stored blocks, the step-by-step decoder
+ * and with it every status and error decision -- and the other warps wait for its commands.
+ * What changes is the lane-parallel round: it runs on WIDE_LANES lanes instead of 32 (same
+ * speculative subsequences, same chain of agreeing lanes, now linked across warps through
+ * shared memory), and the tokens of the chain are turned into bytes by all lanes at once:
+ *
+ *   expand   every lane of the chain writes one 16-bit entry per output byte of its tokens
+ *            into E[]: the byte itself (literals; match bytes whose source lies before the
+ *            round, read from H, a shared-memory mirror of the last 32 KiB of output), or
+ *            the E-index of its source byte (match bytes whose source is produced by the
+ *            same round -- by any lane)
+ *   resolve  pointer jumping, E[x] = E[E[x]] until every entry is a byte: the dependencies
+ *            between the matches of a round are followed by all threads at once in
+ *            O(log depth) sweeps instead of in token order (in place: an entry only ever
+ *            moves towards its source, so a racing reader sees an older but valid link)
+ *   write    four entries -> one aligned 32-bit word to the target and to H
+ *
+ * (reference: decodefast, src/inflator.c:1529-1823 -- one symbol after the other on one core)
+ */
+#ifndef WIDE_WARPS
+#define WIDE_WARPS       16
+#endif
+#define WIDE_LANES       (WIDE_WARPS * 32)
+#define WIDE_E           32768u     /* entries: indices need 15 bits */
+#define WIDE_CAP         (WIDE_E - 8u)
+#define WIDE_H           32768u
+#ifndef WIDE_S0
+#define WIDE_S0          128u
+#endif
+#define E_BYTE           0x8000u
+
+struct WideMem {
+	/* command block: written by the master before the command barrier */
+	uint32_t cmd;                   /* 0: leave, 1: round */
+	uint32_t o, S, endbit, nwords, pre, c, prefix_word;
+	int32_t  delta;
+	uint32_t room, reach;
+	const uint32_t* wbase;
+	uint8_t* dst;                   /* target of this call */
+	uint64_t out;                   /* bytes of this call in front of the round */
+	const uint8_t* history;         /* ring of earlier calls' output, or NULL */
+	uint64_t total_before;
+	uint64_t hist_avail;
+	/* H holds the output positions [h_hi - WIDE_H, h_hi) of this call once h_valid */
+	uint64_t h_hi;
+	uint32_t h_valid;
+	/* results of a round */
+	uint32_t newo, nbytes, lastflag, stepwise, newS;
+	/* scratch */
+	uint32_t anyrun[2], anyjump[2];
+	uint32_t wend[WIDE_WARPS], wflag[WIDE_WARPS], wbrk[WIDE_WARPS], wsb[WIDE_WARPS], wsn[WIDE_WARPS];
+	uint32_t whard[WIDE_WARPS], wcap[WIDE_WARPS], wfull[WIDE_WARPS], wmaxn[WIDE_WARPS];
+	uint32_t inbuf[WIDE_WARPS][INW];
+	uint32_t slots[WIDE_WARPS][PQ_K * 32u];
+	__align__(8) uint16_t E[WIDE_E];
+	__align__(8) uint8_t  H[WIDE_H];
+};
+
+/* all threads of the CTA; the command block is set and a barrier lies behind us */
+static __device__ __noinline__ void
+wide_round(const uint32_t* lit, const uint32_t* dtab, WideMem* w)
+{
+	const unsigned lane = jdb_lane(), wp = jdb_warp(), gl = threadIdx.x;
+	const uint32_t o = w->o, S = w->S, endbit = w->endbit;
+	const uint32_t safe_end = endbit - 64u;
+	uint32_t* const inbuf = w->inbuf[wp];
+	uint32_t* const slots = w->slots[wp] + lane;
+	uint8_t* const dst = w->dst;
+	const uint64_t out = w->out;
+	const uint32_t rbase = (uint32_t) (uintptr_t) dst;
+	const uint32_t a = (uint32_t) ((uintptr_t) (dst + out) & 3u);       /* E-index of the round's first byte */
+
+	/* ---- the history mirror: whatever was produced since the last round (step-by-step
+	 * batches, stored blocks; everything, on the first round of a call) comes from L2 ---- */
+	{
+		int64_t lo = (int64_t) out - (int64_t) WIDE_H;
+		if (w->h_valid && (int64_t) w->h_hi > lo) lo = (int64_t) w->h_hi;
+		for (int64_t p = lo + (int64_t) gl; p < (int64_t) out; p += WIDE_LANES) {
+			uint8_t v = 0;
+			if (p >= 0) v = __ldcg(dst + p);
+			else if (w->history && (uint64_t) (-p) <= w->hist_avail)
+				v = __ldcg(w->history + ((w->total_before + (uint64_t) p) & (JDB_INFLATE_HISTORY - 1)));
+			w->H[(rbase + (uint32_t) p) & (WIDE_H - 1u)] = v;
+		}
+	}
+	/* ---- this warp's part of the input window ---- */
+	{
+		uint32_t b0 = o + 32u * wp * S, b1 = o + 32u * (wp + 1u) * S;
+		if (b0 > safe_end) b0 = safe_end;
+		if (b1 > safe_end) b1 = safe_end;
+		const uint32_t last = ((b1 + 64u) >> 5) + 1u;
+		for (uint32_t k = (b0 >> 5) + lane; k <= last; k += 32u) {
+			uint32_t v = 0;
+			if (k < w->nwords) {
+				const int64_t gi = (int64_t) k + w->delta;
+				if (gi >= 0) v = __ldg(w->wbase + gi);
+				if (k == 0 && w->pre) v = (v & ~(0xffu << (8u * w->c))) | w->prefix_word;
+			}
+			inbuf[k & (INW - 1u)] = v;
+		}
+	}
+	__syncwarp();
+
+	/* ---- speculative decode until the links between neighbours hold (par_round of the
+	 * one-warp decoder, with lane 31 of a warp handing over to lane 0 of the next) ---- */
+	LaneRun r;
+	uint32_t pe = 0, pf = PF_OK;
+	{
+		uint32_t lim = o + (gl + 1u) * S;
+		if (lim > safe_end) lim = safe_end;
+		uint32_t st = o + gl * S;
+		if (st > safe_end) st = safe_end;
+		bool run = true;
+		for (int pass = 0; ; pass++) {
+			if (run) lane_decode(inbuf, lit, dtab, slots, r, st, lim, safe_end);
+			if (lane == 31) { w->wend[wp] = r.end; w->wflag[wp] = r.flag; }
+			__syncthreads();
+			if (gl == 0) w->anyrun[(pass + 1) & 1] = 0;      /* read last before this barrier, set next behind the following one */
+			pe = __shfl_up_sync(JDB_FULL_MASK, r.end, 1);
+			pf = __shfl_up_sync(JDB_FULL_MASK, r.flag, 1);
+			if (lane == 0 && wp > 0) { pe = w->wend[wp - 1]; pf = w->wflag[wp - 1]; }
+			run = gl > 0 && pf == PF_OK && pe != r.start;
+			if (pass + 1 >= PAR_MAXPASS) break;
+			if (__any_sync(JDB_FULL_MASK, run) && lane == 0) w->anyrun[pass & 1] = 1;
+			__syncthreads();
+			if (!w->anyrun[pass & 1]) break;
+			st = pe;
+		}
+	}
+	/* ---- the chain: lanes 0..v-1 ---- */
+	{
+		const bool linked = gl == 0 || (pf == PF_OK && pe == r.start);
+		const unsigned broken = __ballot_sync(JDB_FULL_MASK, !linked);
+		if (lane == 0) w->wbrk[wp] = broken ? (uint32_t) __ffs(broken) - 1u : 32u;
+	}
+	__syncthreads();
+	uint32_t v = WIDE_LANES;
+	for (uint32_t k = 0; k < WIDE_WARPS; k++)
+		if (w->wbrk[k] < 32u) { v = 32u * k + w->wbrk[k]; break; }
+	/* bytes and tokens in front of every lane */
+	uint32_t bincl = gl < v ? r.bytes : 0u;
+	uint32_t nincl = gl < v ? r.n : 0u;
+	for (int k = 1; k < 32; k <<= 1) {
+		const uint32_t tb = __shfl_up_sync(JDB_FULL_MASK, bincl, k);
+		const uint32_t tn = __shfl_up_sync(JDB_FULL_MASK, nincl, k);
+		if ((int) lane >= k) { bincl += tb; nincl += tn; }
+	}
+	if (lane == 31) { w->wsb[wp] = bincl; w->wsn[wp] = nincl; }
+	__syncthreads();
+	for (uint32_t k = 0; k < wp; k++) { bincl += w->wsb[k]; nincl += w->wsn[k]; }
+	/* the target room and the reach of the distances end the chain for the step-by-step
+	 * decoder, the size of E[] ends it for the next round */
+	{
+		const bool hard = gl < v && (bincl > w->room || (int64_t) r.need > (int64_t) w->reach + (int64_t) (bincl - r.bytes));
+		const bool cap = gl < v && a + bincl > WIDE_CAP;
+		const unsigned hm = __ballot_sync(JDB_FULL_MASK, hard), cm = __ballot_sync(JDB_FULL_MASK, cap);
+		if (lane == 0) {
+			w->whard[wp] = hm ? (uint32_t) __ffs(hm) - 1u : 32u;
+			w->wcap[wp] = cm ? (uint32_t) __ffs(cm) - 1u : 32u;
+		}
+	}
+	__syncthreads();
+	uint32_t stepwise = 0, capped = 0;
+	{
+		uint32_t vh = WIDE_LANES, vc = WIDE_LANES;
+		for (uint32_t k = 0; k < WIDE_WARPS; k++)
+			if (w->whard[k] < 32u) { vh = 32u * k + w->whard[k]; break; }
+		for (uint32_t k = 0; k < WIDE_WARPS; k++)
+			if (w->wcap[k] < 32u) { vc = 32u * k + w->wcap[k]; break; }
+		if (vh < v && vh <= vc) { v = vh; stepwise = 1; }
+		else if (vc < v) { v = vc; capped = 1; }
+	}
+	{
+		const unsigned full = __ballot_sync(JDB_FULL_MASK, gl < v && r.flag == PF_FULL);
+		const uint32_t maxn = __reduce_max_sync(JDB_FULL_MASK, gl < v ? r.n : 0u);
+		if (lane == 0) { w->wfull[wp] = full != 0; w->wmaxn[wp] = maxn; }
+	}
+	if (v && gl == v - 1u) {
+		w->newo = r.end;
+		w->nbytes = bincl;
+		w->lastflag = r.flag;
+	}
+	if (v == 0 && gl == 0) {
+		w->newo = o;
+		w->nbytes = 0;
+		w->lastflag = PF_OK;
+	}
+	__syncthreads();
+	const uint32_t nbytes = w->nbytes;
+	if (gl == 0) {
+		/* next round: shorter subsequences when token slots or E[] ran out, longer ones
+		 * again while both stay half empty */
+		uint32_t full = 0, maxn = 0, ns = S;
+		for (uint32_t k = 0; k < WIDE_WARPS; k++) { full |= w->wfull[k]; if (w->wmaxn[k] > maxn) maxn = w->wmaxn[k]; }
+		if (full || capped) ns = S >= PAR_SMIN + 32u ? S - 32u : PAR_SMIN;
+		else if (maxn <= PQ_K / 2u && S < PAR_SMAX && v == WIDE_LANES && nbytes < WIDE_CAP / 2u) ns = S + 32u;
+		w->newS = ns;
+		w->stepwise = stepwise;
+		/* entries outside the round in its first and last quad */
+		for (uint32_t x = 0; x < a; x++) w->E[x] = E_BYTE;
+		for (uint32_t x = a + nbytes; x < ((a + nbytes + 3u) & ~3u); x++) w->E[x] = E_BYTE;
+		w->anyjump[0] = 0;
+		w->anyjump[1] = 0;
+	}
+
+	/* ---- expand ---- */
+	if (gl < v) {
+		uint32_t x = a + bincl - r.bytes;
+		const uint32_t hb = rbase + (uint32_t) out - a;        /* H index of E-index 0 */
+		for (uint32_t i = 0; i < r.n; i++) {
+			const uint32_t tok = slots[i * 32u];
+			const uint32_t len = tok >> 16;
+			if (len == 0) {
+				w->E[x++] = (uint16_t) (E_BYTE | tok);
+				continue;
+			}
+			const uint32_t dist = tok & 0xffffu;
+			if (dist <= x - a) {
+				const uint32_t sx = x - dist;
+				for (uint32_t j = 0; j < len; j++) w->E[x + j] = (uint16_t) (sx + j);
+			} else {
+				for (uint32_t j = 0; j < len; j++) {
+					const int32_t sp = (int32_t) (x + j) - (int32_t) dist;
+					w->E[x + j] = sp >= (int32_t) a ? (uint16_t) sp
+					                                : (uint16_t) (E_BYTE | w->H[(hb + (uint32_t) sp) & (WIDE_H - 1u)]);
+				}
+			}
+			x += len;
+		}
+	}
+	__syncthreads();
+
+	/* ---- resolve ---- */
+	const uint32_t nquad = (a + nbytes + 3u) >> 2;
+	uint64_t* const E4 = (uint64_t*) w->E;
+	for (uint32_t it = 0; nbytes; it++) {
+		bool more = false;
+		for (uint32_t q = gl; q < nquad; q += WIDE_LANES) {
+			uint64_t e4 = E4[q];
+			if ((e4 & 0x8000800080008000ull) == 0x8000800080008000ull) continue;
+#pragma unroll
+			for (uint32_t k = 0; k < 4; k++) {
+				const uint32_t e = (uint32_t) (e4 >> (16u * k)) & 0xffffu;
+				if (e & E_BYTE) continue;
+				const uint32_t f = w->E[e];
+				if (!(f & E_BYTE)) more = true;
+				e4 = (e4 & ~(0xffffull << (16u * k))) | ((uint64_t) f << (16u * k));
+			}
+			E4[q] = e4;
+		}
+		if (__any_sync(JDB_FULL_MASK, more) && lane == 0) w->anyjump[it & 1] = 1;
+		__syncthreads();
+		const uint32_t again = w->anyjump[it & 1];
+		if (gl == 0) w->anyjump[(it + 1) & 1] = 0;
+		if (!again) break;
+		/* (the flag of sweep it + 1 was cleared before the barrier of sweep it - 1 ... it is
+		 * cleared here, after everybody's read of sweep it - 1's and before anybody's
+		 * write of sweep it + 1's, which lies behind the next barrier) */
+		__syncthreads();
+	}
+
+	/* ---- write: target and mirror ---- */
+	{
+		uint8_t* const dal = dst + out - a;                       /* 4-byte aligned */
+		const uint32_t hal = rbase + (uint32_t) out - a;
+		for (uint32_t q = gl; q < nquad; q += WIDE_LANES) {
+			const uint64_t e4 = E4[q];
+			const uint32_t word = (uint32_t) (e4 & 0xffu) | ((uint32_t) (e4 >> 8) & 0xff00u) |
+			                      ((uint32_t) (e4 >> 16) & 0xff0000u) | ((uint32_t) (e4 >> 24) & 0xff000000u);
+			const uint32_t x0 = 4u * q;
+			if (x0 >= a && x0 + 4u <= a + nbytes) {
+				*(uint32_t*) (dal + x0) = word;
+				*(uint32_t*) (w->H + ((hal + x0) & (WIDE_H - 1u))) = word;
+			} else {
+				for (uint32_t k = 0; k < 4; k++) {
+					const uint32_t x = x0 + k;
+					if (x >= a && x < a + nbytes) {
+						const uint8_t b = (uint8_t) (word >> (8u * k));
+						dal[x] = b;
+						w->H[(hal + x) & (WIDE_H - 1u)] = b;
+					}
+				}
+			}
+		}
+	}
+	if (gl == 0) {
+		w->h_hi = out + nbytes;
+		w->h_valid = 1;
+	}
+	__syncthreads();
+}
+
 /*
  * Decode one stream (or one call's worth of a streaming decode).
  * Called by all 32 lanes of a warp with identical arguments.
  */
+template <bool WIDE>
 static __device__ void
-inflate_stream(WarpMem* m, Stream& s)
+inflate_stream(WarpMem* m, Stream& s, WideMem* w)
 {
 	const unsigned lane = jdb_lane();
 	Bits b;
@@ -866,8 +1166,9 @@ inflate_stream(WarpMem* m, Stream& s)
 			uint32_t o = pre ? 8u * c + 8u - b.bc : 8u * al;
 			uint32_t filled = 0;
 
-			uint32_t S = PAR_S0;              /* subsequence length of the lane-parallel rounds */
+			uint32_t S = WIDE ? WIDE_S0 : PAR_S0;   /* subsequence length of the lane-parallel rounds */
 			bool step_by_step = false;        /* the next batch goes through the step-by-step decoder */
+			uint32_t wide_ev = 0;             /* how the last wide round ended (acted on once the master's own input ring follows) */
 			for (;;) {
 				/* ---- all lanes: keep the input of one lane-parallel round (or >= 3 KiBit) ahead
 				 * of `o` in the ring ---- */
@@ -885,6 +1186,7 @@ inflate_stream(WarpMem* m, Stream& s)
 					filled += 1024u;
 				}
 				__syncwarp();
+				if (WIDE && wide_ev) { ev = wide_ev; break; }
 
 				/* ---- lane-parallel round --------------------------------------------------
 				 * Lane l decodes the symbols that start in bits [o + l*S, o + (l+1)*S) of the
@@ -909,7 +1211,40 @@ inflate_stream(WarpMem* m, Stream& s)
 					pend_len = 0;
 				} else
 #ifndef PAR_OFF
-				if (!step_by_step && endbit - o >= 2u * S + 64u) {
+				if (WIDE && !step_by_step && endbit - o >= 2u * S + 64u) {
+					/* ---- the round on all warps of the CTA (wide_round): everything produced so
+					 * far goes to the target first, the round writes behind it ---- */
+					flush_ring(s, s.out, true);
+					if (lane == 0) {
+						const uint64_t room64 = s.dst_cap - s.out;
+						const uint64_t reach64 = s.out + s.hist_avail;
+						w->cmd = 1;
+						w->o = o; w->S = S; w->endbit = endbit; w->nwords = nwords;
+						w->pre = pre; w->c = c; w->prefix_word = prefix_word; w->delta = delta;
+						w->room = room64 > 0xfffff000ull ? 0xfffff000u : (uint32_t) room64;
+						w->reach = reach64 > 0x10000ull ? 0x10000u : (uint32_t) reach64;
+						w->wbase = wbase;
+						w->dst = s.dst; w->out = s.out;
+						w->history = s.st ? s.st->history : (const uint8_t*) 0;
+						w->total_before = s.total_before;
+						w->hist_avail = s.hist_avail;
+						w->anyrun[0] = 0; w->anyrun[1] = 0;
+					}
+					__syncthreads();
+					wide_round(m->lit, m->dist, w);
+					const uint32_t newo = w->newo, nb = w->nbytes, lastflag = w->lastflag;
+					S = w->newS;
+					if (nb) {
+						s.out += nb;
+						s.flushed = s.out;
+						s.ring_lo = (int64_t) s.out;       /* the master's ring holds none of these bytes */
+					}
+					if (lastflag == PF_ANOM || newo == o || w->stepwise) step_by_step = true;
+					o = newo;
+					wide_ev = lastflag == PF_EOB ? 1u : 0u;
+					continue;
+				} else
+				if (!WIDE && !step_by_step && endbit - o >= 2u * S + 64u) {
 					const uint32_t safe_end = endbit - 64u;
 					const uint64_t room64 = s.dst_cap - s.out;
 					const uint32_t room = room64 > 0xfffff000ull ? 0xfffff000u : (uint32_t) room64;
@@ -924,7 +1259,7 @@ inflate_stream(WarpMem* m, Stream& s)
 						if (st > safe_end) st = safe_end;
 						bool run = true;
 						for (int pass = 0; ; pass++) {
-							if (run) lane_decode(m, slots, r, st, lim, safe_end);
+							if (run) lane_decode(m->inbuf, m->lit, m->dist, slots, r, st, lim, safe_end);
 							if (pass + 1 >= PAR_MAXPASS) break;
 							const uint32_t pe = __shfl_up_sync(JDB_FULL_MASK, r.end, 1);
 							const uint32_t pf = __shfl_up_sync(JDB_FULL_MASK, r.flag, 1);
@@ -1242,7 +1577,7 @@ inflate_batch_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__
 		if (!zerr) {
 			s.src += head;
 			s.src_len -= head;
-			inflate_stream(m, s);
+			inflate_stream<false>(m, s, (WideMem*) 0);
 			r.status = s.status;
 			r.error = s.error;
 			r.consumed = s.consumed + head;
@@ -1263,6 +1598,65 @@ inflate_batch_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__
 		if (lane == 0) results[idx] = r;
 		__syncwarp();
 	}
+}
+
+/*
+ * One CTA per stream: warp 0 decodes (inflate_stream), the other warps serve its wide rounds.
+ * Raw DEFLATE only -- this is the kernel behind inflator_inflate for a stream without chunk
+ * markers (container framing is zstrm's business on the host).
+ */
+__global__ void __launch_bounds__(WIDE_LANES, 1)
+inflate_wide_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ dst_base,
+                    const jdb_inflate_item* __restrict__ items, jdb_inflate_result* __restrict__ results,
+                    jdb_inflate_state* states, uint32_t final)
+{
+	JDB_DYN_SMEM(smem_raw);
+	WarpMem* m = (WarpMem*) smem_raw;
+	WideMem* w = (WideMem*) (smem_raw + ((sizeof(WarpMem) + 15u) & ~(size_t) 15u));
+	const unsigned lane = jdb_lane();
+	const uint32_t idx = blockIdx.x;
+
+	if (jdb_warp() != 0) {
+		for (;;) {
+			__syncthreads();
+			if (w->cmd == 0) break;
+			wide_round(m->lit, m->dist, w);
+		}
+		return;
+	}
+	if (lane == 0) { w->h_valid = 0; w->h_hi = 0; }
+	__syncwarp();
+	const jdb_inflate_item it = items[idx];
+	Stream s;
+	s.src = src_base + it.src_off;
+	s.src_len = it.src_len;
+	s.dst = dst_base + it.dst_off;
+	s.dst_cap = it.dst_cap;
+	s.final = (int) final;
+	s.count_only = 0;
+	s.stop_marker = 0;
+	s.st = states ? states + idx : NULL;
+	inflate_stream<true>(m, s, w);
+	jdb_inflate_result r;
+	r.status = s.status; r.error = s.error; r.zerror = 0; r.checksum = 0;
+	r.consumed = s.consumed; r.produced = s.out;
+	if (lane == 0) {
+		results[idx] = r;
+		w->cmd = 0;
+	}
+	__syncthreads();
+}
+
+extern "C" int jdb_inflate_wide(const uint8_t* src_base, uint8_t* dst_base,
+                                const jdb_inflate_item* items, jdb_inflate_result* results,
+                                jdb_inflate_state* states, uint32_t count, uint32_t final, jdb_stream s)
+{
+	if (count == 0) return JDB_OK;
+	const size_t smem = ((sizeof(WarpMem) + 15u) & ~(size_t) 15u) + sizeof(WideMem);
+	JDB_CONFIGURE_SMEM(inflate_wide_kernel, smem);
+	JDB_LAUNCH(inflate_wide_kernel, dim3(count), dim3(WIDE_LANES), smem, s,
+	           src_base, dst_base, items, results, states, final);
+	return jdb_rt_check_launch("inflate_wide_kernel");
 }
 
 extern "C" size_t jdb_inflate_state_bytes(void) { return sizeof(jdb_inflate_state); }

@@ -156,6 +156,15 @@ int jdb_inflate_batch(const uint8_t* src_base, uint8_t* dst_base,
                       jdb_inflate_state* states, uint32_t count, uint32_t format,
                       uint32_t final, uint32_t* counter, jdb_stream s);
 
+/*
+ * The same for streams that deserve a whole CTA each (inflate_wide_kernel): one resumable raw
+ * DEFLATE stream per item, `count` CTAs.  This is what inflator_inflate runs for a stream
+ * that carries no chunk markers.
+ */
+int jdb_inflate_wide(const uint8_t* src_base, uint8_t* dst_base,
+                     const jdb_inflate_item* items, jdb_inflate_result* results,
+                     jdb_inflate_state* states, uint32_t count, uint32_t final, jdb_stream s);
+
 /* chunk discovery for the parallel decode of one large stream (inflate.cu) */
 int jdb_marker_scan(const uint8_t* src, uint64_t n, uint32_t* ends, uint32_t max_ends,
                     uint32_t* count, jdb_stream s);

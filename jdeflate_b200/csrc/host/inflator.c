@@ -86,6 +86,8 @@ struct TINFLTPrvt {
 	size_t leftover;        /* bytes after the end of the stream that came from earlier source windows: they
 	                         * sit at inq[inqoff ..) until zstrm takes them back or the next reset */
 	jdb_dbuf   outbuf;
+	int        narrow;      /* JDB200_INFLATE_NARROW=1 (read at create): one warp instead of a CTA for the
+	                         * sequential decoder -- the round-1 shape, kept for measurements */
 
 	jdb_inflate_state* dstate;
 	/* pinned: item + result; device mirrors */
@@ -137,6 +139,10 @@ inflator_create(uintxx flags, const TAllocator* allctr)
 	memset(state, 0, sizeof(struct TINFLTPrvt));
 	PRVT->allctr = allctr;
 	PRVT->device = jdb_rt_current_device();
+	{
+		const char* e = getenv("JDB200_INFLATE_NARROW");
+		PRVT->narrow = e != NULL && e[0] == '1';
+	}
 
 	if (jdb_stream_create(&PRVT->stream) != JDB_OK) {
 		goto L_FAIL;
@@ -872,9 +878,12 @@ inflator_inflate(TInflator* state, uint32 final)
 		}
 
 		if (jdb_copy_async(D_ITEM(PRVT), item, sizeof(*item), PRVT->stream) != JDB_OK ||
-		    jdb_inflate_batch(PRVT->inq.ptr, dst, D_ITEM(PRVT), D_RESULT(PRVT), PRVT->dstate, 1,
-		                      JDB_FMT_RAW, (uint32_t) (PBLC->finalinput && absorbed_all),
-		                      D_COUNTER(PRVT), PRVT->stream) != JDB_OK ||
+		    (PRVT->narrow
+		         ? jdb_inflate_batch(PRVT->inq.ptr, dst, D_ITEM(PRVT), D_RESULT(PRVT), PRVT->dstate, 1,
+		                             JDB_FMT_RAW, (uint32_t) (PBLC->finalinput && absorbed_all),
+		                             D_COUNTER(PRVT), PRVT->stream)
+		         : jdb_inflate_wide(PRVT->inq.ptr, dst, D_ITEM(PRVT), D_RESULT(PRVT), PRVT->dstate, 1,
+		                            (uint32_t) (PBLC->finalinput && absorbed_all), PRVT->stream)) != JDB_OK ||
 		    jdb_copy_async(res, D_RESULT(PRVT), sizeof(*res), PRVT->stream) != JDB_OK ||
 		    jdb_stream_sync(PRVT->stream) != JDB_OK) {
 			poison(PRVT, INFLT_EBADSTATE);
