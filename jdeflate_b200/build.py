@@ -127,7 +127,8 @@ def build_emu(force: bool = False, sanitize: bool = False) -> Path:
     cxxflags = ["-std=c++17", "-O1", "-g", "-fPIC", "-DJDB_SIMT_EMU", "-Wall", "-Wno-unused-function",
                 "-Wno-unknown-pragmas", "-Wno-unused-variable", "-Wno-sign-compare",
                 "-Wno-unused-but-set-variable", *san,
-                "-I", EMU_DIR, "-I", INCLUDE, "-I", CSRC / "device"]
+                "-I", EMU_DIR, "-I", INCLUDE, "-I", CSRC / "device",
+                *os.environ.get("JDB_EMU_EXTRA", "").split()]
     jobs, objs = [], []
     for src in device_sources():
         if src.name == "runtime.cu":

@@ -49,6 +49,20 @@ extern "C" void jdb_prof_end(int slot, jdb_stream s);
 static __device__ __forceinline__ unsigned jdb_lane() { return threadIdx.x & 31u; }
 static __device__ __forceinline__ unsigned jdb_warp() { return threadIdx.x >> 5; }
 
+/* A pointer into shared memory whose address the compiler takes from a register instead of
+ * rebuilding it where it is used: sm_100 shared addresses carry the CTA's rank in its cluster
+ * (S2R SR_CgaCtaId), and ptxas is happy to re-read that special register inside a hot loop. */
+template <typename T> static __device__ __forceinline__ T* jdb_pin_shared(T* p)
+{
+#ifndef JDB_SIMT_EMU
+	uint32_t a = (uint32_t) __cvta_generic_to_shared((const void*) p);
+	asm volatile("" : "+r"(a));
+	return (T*) __cvta_shared_to_generic((size_t) a);
+#else
+	return p;
+#endif
+}
+
 /* unaligned little-endian 32 bit read assembled from two aligned words */
 static __device__ __forceinline__ uint32_t jdb_ld32u(const uint8_t* base, uint32_t off)
 {

@@ -33,6 +33,9 @@
  * "deviations") are rejected with INFLT_EBADCODE like zlib does.
  */
 #include "common.cuh"
+#ifdef WIDE_PROF
+#include <stdio.h>
+#endif
 
 #ifndef INF_WARPS
 #define INF_WARPS        16
@@ -121,12 +124,14 @@ __constant__ uint8_t c_precode_order[19] = {
 
 /* per-warp shared memory */
 /* scratch of the header parser / table builder (one per warp) */
+#define HDR_STAGE 640u     /* >= the longest block header: 3 + 14 + 19 * 3 + 316 * 14 bits = 563 bytes */
 struct BuildMem {
 	uint16_t code[320];
 	uint8_t  len[320];
-	uint16_t count[16];
-	uint16_t next[16];
+	uint32_t count[16];
+	uint32_t next[16];
 	uint32_t scratch[8];
+	uint8_t  hdr[HDR_STAGE];       /* the bytes of the header, staged by all lanes for lane 0's bit reader */
 };
 
 struct WarpMem {
@@ -159,11 +164,12 @@ build_table(BuildMem* m, uint32_t* table, int n, int kind, int lenoff)
 	for (int i = lane; i < limit; i += 32) table[i] = 0;
 	if (lane < 16) m->count[lane] = 0;
 	__syncwarp();
+	for (int i = lane; i < n; i += 32) atomicAdd(&m->count[len[i]], 1u);
+	__syncwarp();
 
 	int rc = 0;
 	if (lane == 0) {
-		for (int i = 0; i < n; i++) m->count[len[i]]++;
-		if (m->count[0] == n) {
+		if (m->count[0] == (uint32_t) n) {
 			rc = kind == KIND_DIST ? 2 : 1;         /* 2: empty distance code is legal */
 		} else {
 			m->count[0] = 0;
@@ -171,7 +177,7 @@ build_table(BuildMem* m, uint32_t* table, int n, int kind, int lenoff)
 			while (m->count[mlen] == 0) mlen--;
 			int left = 1;
 			for (int l = 1; l <= 15; l++) {
-				left = (left << 1) - m->count[l];
+				left = (left << 1) - (int) m->count[l];
 				if (left < 0) { rc = 1; break; }
 			}
 			if (rc == 0 && left && !(mlen == 1 && kind == KIND_DIST)) rc = 1;
@@ -180,18 +186,26 @@ build_table(BuildMem* m, uint32_t* table, int n, int kind, int lenoff)
 				m->next[0] = 0;
 				for (int l = 1; l <= 15; l++) {
 					c = (c + m->count[l - 1]) << 1;
-					m->next[l] = (uint16_t) c;
-				}
-				/* canonical code of every symbol, bit reversed (LSB-first stream) */
-				for (int i = 0; i < n; i++) {
-					int l = len[i];
-					if (l) m->code[i] = (uint16_t) (__brev((uint32_t) m->next[l]++) >> (32 - l));
+					m->next[l] = c;
 				}
 			}
 		}
 	}
 	rc = __shfl_sync(JDB_FULL_MASK, rc, 0);
 	if (rc) return rc == 2 ? 0 : 1;
+	/* canonical code of every symbol, bit reversed (LSB-first stream): symbols of one length
+	 * take consecutive codes in symbol order -- 32 symbols at a time, a symbol's rank among
+	 * the lanes that hold the same length on top of the running count of that length */
+	for (int base = 0; base < n; base += 32) {
+		const int i = base + (int) lane;
+		const int l = i < n ? len[i] : 0;
+		const unsigned peers = __match_any_sync(JDB_FULL_MASK, l);
+		const uint32_t rank = (uint32_t) __popc(peers & ((1u << lane) - 1u));
+		if (l) m->code[i] = (uint16_t) (__brev(m->next[l] + rank) >> (32 - l));
+		__syncwarp();
+		if (l && rank == 0) m->next[l] += (uint32_t) __popc(peers);
+		__syncwarp();
+	}
 
 	const uint32_t rootmask = (1u << root) - 1;
 
@@ -336,11 +350,24 @@ lookup32(const uint32_t* table, uint32_t bits, int root)
  * come back on all lanes; a stored block's length is left in bm->scratch[0].
  */
 static __device__ uint32_t
-parse_block_header(BuildMem* bm, uint32_t* lit, uint32_t* dist, Bits& b, uint32_t& type_out, uint32_t& lb_out)
+parse_block_header(BuildMem* bm, uint32_t* lit, uint32_t* dist, Bits& gb_, uint32_t& type_out, uint32_t& lb_out)
 {
 	const unsigned lane = jdb_lane();
 	uint32_t r = 0;        /* 0 ok, 1 starved, 2+ : INFLT error code + 1 */
 	uint32_t type = 0, lb = 0, hlit = 0, hdist = 0;
+	/* lane 0 reads the header bit by bit: from shared memory, where all lanes put the next
+	 * HDR_STAGE bytes of the input first (no header is longer), not byte by byte from L2 */
+	Bits& gb = gb_;
+	const uint8_t* const gp = gb.p;
+	{
+		const uint64_t left = (uint64_t) (gb.end - gb.p);
+		const uint32_t gn = left < HDR_STAGE ? (uint32_t) left : HDR_STAGE;
+		for (uint32_t i = lane; i < gn; i += 32) bm->hdr[i] = gp[i];
+		__syncwarp();
+	}
+	Bits b = gb;
+	b.p = bm->hdr;
+	b.end = bm->hdr + ((uint64_t) (gb.end - gb.p) < HDR_STAGE ? (uint64_t) (gb.end - gb.p) : (uint64_t) HDR_STAGE);
 	if (lane == 0) {
 		if (!bits_need(b, 3)) r = 1;
 		else {
@@ -437,6 +464,9 @@ parse_block_header(BuildMem* bm, uint32_t* lit, uint32_t* dist, Bits& b, uint32_
 				r = 1 + E_BADTREE;
 		}
 	}
+	gb.bb = b.bb;
+	gb.bc = b.bc;
+	gb.p = gp + (b.p - bm->hdr);
 	type_out = type;
 	lb_out = lb;
 	return r;
@@ -713,14 +743,131 @@ lane_decode(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, ui
 #ifndef WIDE_WARPS
 #define WIDE_WARPS       16
 #endif
+#ifndef WIDE_LEAD
+#define WIDE_LEAD        0u         /* bits a lane decodes in front of its subsequence before its first guess */
+#endif
+#ifndef WIDE_MAXPASS
+#define WIDE_MAXPASS     12
+#endif
 #define WIDE_LANES       (WIDE_WARPS * 32)
 #define WIDE_E           32768u     /* entries: indices need 15 bits */
 #define WIDE_CAP         (WIDE_E - 8u)
 #define WIDE_H           32768u
 #ifndef WIDE_S0
-#define WIDE_S0          128u
+#define WIDE_S0          160u
 #endif
 #define E_BYTE           0x8000u
+#ifndef WIDE_LONG
+#define WIDE_LONG        24u        /* longer matches are expanded by all lanes of a warp */
+#endif
+
+/*
+ * lane_decode for the wide rounds, where the latency of ONE warp's pass is what a round waits
+ * for.  Called by all lanes of a warp (`run`: this lane takes part).  Two differences to
+ * lane_decode: the three input words around the position stay in registers (a peek is one funnel
+ * shift, the ring is read when the position enters the next word); and the loop is closed by a
+ * vote, one symbol per trip for every lane still at work -- a loop that lanes leave one by one
+ * through breaks is compiled without a reconvergence point behind the literal / match branch
+ * by some builds, after which the lanes of a warp run its trips in ever smaller groups, one
+ * group after the other (measured: 3x the time of a pass).
+ */
+static __device__ __forceinline__ void
+lane_decode_w(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, uint32_t* slots, LaneRun& r,
+              bool run, uint32_t start, uint32_t limit, uint32_t safe_end)
+{
+	uint32_t pos = start, n = 0, bytes = 0, flag = PF_OK;
+	int32_t need = 0;
+	uint32_t cur = pos >> 5;
+	uint32_t w0 = inbuf[cur & (INW - 1u)], w1 = inbuf[(cur + 1u) & (INW - 1u)], w2 = inbuf[(cur + 2u) & (INW - 1u)];
+	bool act = run && pos < limit;
+	while (__any_sync(JDB_FULL_MASK, act)) {
+		if (act) {
+			if (n >= PQ_K) {
+				flag = PF_FULL;
+				act = false;
+			} else {
+				const uint32_t i = pos >> 5;
+				if (i != cur) {
+					if (i == cur + 1u) { w0 = w1; w1 = w2; }
+					else { w0 = inbuf[i & (INW - 1u)]; w1 = inbuf[(i + 1u) & (INW - 1u)]; }
+					w2 = inbuf[(i + 2u) & (INW - 1u)];
+					cur = i;
+				}
+				const uint32_t bits = __funnelshift_r(w0, w1, pos);
+				const uint32_t e = lookup32(lit, bits, LIT_ROOT);
+				const uint32_t nb = e & 15u;
+				const uint32_t type = (e >> 8) & 3u;
+				uint32_t tok = 0;
+				if (nb == 0) {
+					flag = PF_ANOM;
+					act = false;
+				} else if (type == T_LIT) {
+					tok = e >> 16;
+					pos += nb;
+					bytes += 1;
+				} else if (type == T_BASE) {
+					const uint32_t lxb = (e >> 4) & 15u;
+					const uint32_t len = (e >> 16) + ((bits >> nb) & ((1u << lxb) - 1u));
+					const uint32_t o2 = pos + nb + lxb;          /* in this word or the next */
+					const uint32_t bits2 = (o2 >> 5) == cur ? __funnelshift_r(w0, w1, o2) : __funnelshift_r(w1, w2, o2);
+					const uint32_t d = lookup32(dtab, bits2, DIST_ROOT);
+					const uint32_t dnb = d & 15u, dxb = (d >> 4) & 15u;
+					if ((e >> 16) == 0 || dnb == 0 || (d >> 16) == 0) {
+						flag = PF_ANOM;
+						act = false;
+					} else {
+						const uint32_t dist = (d >> 16) + ((bits2 >> dnb) & ((1u << dxb) - 1u));
+						const int32_t nd = (int32_t) dist - (int32_t) bytes;
+						if (nd > need) need = nd;
+						tok = (len << 16) | dist;
+						pos = o2 + dnb + dxb;
+						bytes += len;
+					}
+				} else {
+					pos += nb;
+					flag = PF_EOB;
+					act = false;
+				}
+				if (act) {
+					slots[n * 32u] = tok;
+					n++;
+					act = pos < limit;
+				}
+			}
+		}
+	}
+	if (run) {
+		if (flag == PF_OK && limit == safe_end) flag = PF_STOP;
+		r.start = start; r.end = pos; r.n = n; r.bytes = bytes; r.flag = flag; r.need = need;
+	}
+}
+
+/*
+ * Lead-in of a speculative lane: walk symbols from `start` without recording anything and return
+ * the first symbol boundary at or behind `boundary`.  A lane that has already decoded a stretch in
+ * front of its subsequence has most likely fallen into step with the true symbol sequence by the
+ * time it reaches it, so that its first guess links with its predecessor.  Anything unusual on
+ * the way: give up and guess the boundary itself.
+ */
+static __device__ __forceinline__ uint32_t
+lane_lead_in(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, uint32_t start, uint32_t boundary)
+{
+	uint32_t pos = start;
+	while (pos < boundary) {
+		const uint32_t bits = peek32(inbuf, pos);
+		const uint32_t e = lookup32(lit, bits, LIT_ROOT);
+		const uint32_t nb = e & 15u;
+		const uint32_t type = (e >> 8) & 3u;
+		if (nb == 0) return boundary;
+		if (type == T_LIT) { pos += nb; continue; }
+		if (type != T_BASE || (e >> 16) == 0) return boundary;
+		const uint32_t o2 = pos + nb + ((e >> 4) & 15u);
+		const uint32_t d = lookup32(dtab, peek32(inbuf, o2), DIST_ROOT);
+		if ((d & 15u) == 0 || (d >> 16) == 0) return boundary;
+		pos = o2 + (d & 15u) + ((d >> 4) & 15u);
+	}
+	return pos;
+}
 
 struct WideMem {
 	/* command block: written by the master before the command barrier */
@@ -740,19 +887,36 @@ struct WideMem {
 	/* results of a round */
 	uint32_t newo, nbytes, lastflag, stepwise, newS;
 	/* scratch */
-	uint32_t anyrun[2], anyjump[2];
 	uint32_t wend[WIDE_WARPS], wflag[WIDE_WARPS], wbrk[WIDE_WARPS], wsb[WIDE_WARPS], wsn[WIDE_WARPS];
 	uint32_t whard[WIDE_WARPS], wcap[WIDE_WARPS], wfull[WIDE_WARPS], wmaxn[WIDE_WARPS];
 	uint32_t inbuf[WIDE_WARPS][INW];
 	uint32_t slots[WIDE_WARPS][PQ_K * 32u];
 	__align__(8) uint16_t E[WIDE_E];
 	__align__(8) uint8_t  H[WIDE_H];
+#ifdef WIDE_PROF
+	long long pt[12];               /* cycles per phase (thread 0), rounds, passes, sweeps, bytes */
+	long long runs[16];             /* lanes that decoded in pass k */
+	long long pcyc[16];             /* cycles of pass k */
+	long long t_pass;
+	long long t_last;
+#endif
 };
+
+#ifdef WIDE_PROF
+#define WPROF(k) do { if (threadIdx.x == 0) { const long long t_ = clock64(); w->pt[k] += t_ - w->t_last; w->t_last = t_; } } while (0)
+#define WCOUNT(k, n) do { if (threadIdx.x == 0) w->pt[k] += (n); } while (0)
+#else
+#define WPROF(k) do { } while (0)
+#define WCOUNT(k, n) do { } while (0)
+#endif
 
 /* all threads of the CTA; the command block is set and a barrier lies behind us */
 static __device__ __noinline__ void
-wide_round(const uint32_t* lit, const uint32_t* dtab, WideMem* w)
+wide_round(const uint32_t* lit_, const uint32_t* dtab_, WideMem* w_)
 {
+	const uint32_t* const lit = jdb_pin_shared(lit_);
+	const uint32_t* const dtab = jdb_pin_shared(dtab_);
+	WideMem* const w = jdb_pin_shared(w_);
 	const unsigned lane = jdb_lane(), wp = jdb_warp(), gl = threadIdx.x;
 	const uint32_t o = w->o, S = w->S, endbit = w->endbit;
 	const uint32_t safe_end = endbit - 64u;
@@ -762,6 +926,7 @@ wide_round(const uint32_t* lit, const uint32_t* dtab, WideMem* w)
 	const uint64_t out = w->out;
 	const uint32_t rbase = (uint32_t) (uintptr_t) dst;
 	const uint32_t a = (uint32_t) ((uintptr_t) (dst + out) & 3u);       /* E-index of the round's first byte */
+	WPROF(0);           /* master between rounds */
 
 	/* ---- the history mirror: whatever was produced since the last round (step-by-step
 	 * batches, stored blocks; everything, on the first round of a call) comes from L2 ---- */
@@ -779,6 +944,7 @@ wide_round(const uint32_t* lit, const uint32_t* dtab, WideMem* w)
 	/* ---- this warp's part of the input window ---- */
 	{
 		uint32_t b0 = o + 32u * wp * S, b1 = o + 32u * (wp + 1u) * S;
+		b0 = b0 >= o + WIDE_LEAD ? b0 - WIDE_LEAD : o;
 		if (b0 > safe_end) b0 = safe_end;
 		if (b1 > safe_end) b1 = safe_end;
 		const uint32_t last = ((b1 + 64u) >> 5) + 1u;
@@ -793,6 +959,7 @@ wide_round(const uint32_t* lit, const uint32_t* dtab, WideMem* w)
 		}
 	}
 	__syncwarp();
+	WPROF(1);           /* mirror + staging */
 
 	/* ---- speculative decode until the links between neighbours hold (par_round of the
 	 * one-warp decoder, with lane 31 of a warp handing over to lane 0 of the next) ---- */
@@ -803,23 +970,30 @@ wide_round(const uint32_t* lit, const uint32_t* dtab, WideMem* w)
 		if (lim > safe_end) lim = safe_end;
 		uint32_t st = o + gl * S;
 		if (st > safe_end) st = safe_end;
+		else if (gl) st = lane_lead_in(inbuf, lit, dtab, st >= o + WIDE_LEAD ? st - WIDE_LEAD : o, st);
+		if (st > safe_end) st = safe_end;
 		bool run = true;
 		for (int pass = 0; ; pass++) {
-			if (run) lane_decode(inbuf, lit, dtab, slots, r, st, lim, safe_end);
+#ifdef WIDE_PROF
+			if (gl == 0) { const long long t_ = clock64(); if (pass) w->pcyc[pass < 16 ? pass - 1 : 15] += t_ - w->t_pass; w->t_pass = t_; }
+#endif
+			lane_decode_w(inbuf, lit, dtab, slots, r, run, st, lim, safe_end);
+			WCOUNT(9, 1);
+#ifdef WIDE_PROF
+			if (run) atomicAdd((unsigned long long*) &w->runs[pass < 15 ? pass : 15], 1ull);
+#endif
 			if (lane == 31) { w->wend[wp] = r.end; w->wflag[wp] = r.flag; }
 			__syncthreads();
-			if (gl == 0) w->anyrun[(pass + 1) & 1] = 0;      /* read last before this barrier, set next behind the following one */
 			pe = __shfl_up_sync(JDB_FULL_MASK, r.end, 1);
 			pf = __shfl_up_sync(JDB_FULL_MASK, r.flag, 1);
 			if (lane == 0 && wp > 0) { pe = w->wend[wp - 1]; pf = w->wflag[wp - 1]; }
 			run = gl > 0 && pf == PF_OK && pe != r.start;
-			if (pass + 1 >= PAR_MAXPASS) break;
-			if (__any_sync(JDB_FULL_MASK, run) && lane == 0) w->anyrun[pass & 1] = 1;
-			__syncthreads();
-			if (!w->anyrun[pass & 1]) break;
+			if (pass + 1 >= WIDE_MAXPASS) break;
+			if (!__syncthreads_or(run)) break;
 			st = pe;
 		}
 	}
+	WPROF(2);           /* decode passes */
 	/* ---- the chain: lanes 0..v-1 ---- */
 	{
 		const bool linked = gl == 0 || (pf == PF_OK && pe == r.start);
@@ -886,80 +1060,106 @@ wide_round(const uint32_t* lit, const uint32_t* dtab, WideMem* w)
 		uint32_t full = 0, maxn = 0, ns = S;
 		for (uint32_t k = 0; k < WIDE_WARPS; k++) { full |= w->wfull[k]; if (w->wmaxn[k] > maxn) maxn = w->wmaxn[k]; }
 		if (full || capped) ns = S >= PAR_SMIN + 32u ? S - 32u : PAR_SMIN;
-		else if (maxn <= PQ_K / 2u && S < PAR_SMAX && v == WIDE_LANES && nbytes < WIDE_CAP / 2u) ns = S + 32u;
+		else if (maxn <= 3u * PQ_K / 4u && S < PAR_SMAX && v >= 32u &&
+		         (uint64_t) nbytes * WIDE_LANES * (S + 32u) < (uint64_t) (WIDE_CAP - WIDE_CAP / 8u) * v * S) ns = S + 32u;
 		w->newS = ns;
 		w->stepwise = stepwise;
 		/* entries outside the round in its first and last quad */
 		for (uint32_t x = 0; x < a; x++) w->E[x] = E_BYTE;
 		for (uint32_t x = a + nbytes; x < ((a + nbytes + 3u) & ~3u); x++) w->E[x] = E_BYTE;
-		w->anyjump[0] = 0;
-		w->anyjump[1] = 0;
 	}
 
-	/* ---- expand ---- */
-	if (gl < v) {
-		uint32_t x = a + bincl - r.bytes;
+	WPROF(3);           /* chain, sums, cuts */
+	/* ---- expand: one entry per trip of ONE loop, so that the lanes of a warp, whose tokens
+	 * differ in kind and length, stay together (a loop per token would run as long as the
+	 * longest token of every step); matches longer than WIDE_LONG bytes are left out here and
+	 * written by all lanes of the warp afterwards ---- */
+	{
 		const uint32_t hb = rbase + (uint32_t) out - a;        /* H index of E-index 0 */
-		for (uint32_t i = 0; i < r.n; i++) {
-			const uint32_t tok = slots[i * 32u];
-			const uint32_t len = tok >> 16;
-			if (len == 0) {
-				w->E[x++] = (uint16_t) (E_BYTE | tok);
-				continue;
+		const uint32_t mybytes = gl < v ? r.bytes : 0u;
+		const uint32_t myn = gl < v ? r.n : 0u;
+		const uint32_t x0 = a + bincl - mybytes;
+		{
+			uint32_t x = x0, i = 0, left = 0;
+			int32_t back = 0;             /* distance of the match in hand */
+			while (__any_sync(JDB_FULL_MASK, i < myn || left)) {
+				if (!(i < myn || left)) continue;
+				if (left == 0) {
+					const uint32_t tok = slots[i * 32u];
+					i++;
+					const uint32_t len = tok >> 16;
+					if (len == 0) {
+						w->E[x++] = (uint16_t) (E_BYTE | tok);
+						continue;
+					}
+					if (len > WIDE_LONG) { x += len; continue; }
+					left = len;
+					back = (int32_t) (tok & 0xffffu);
+				}
+				const int32_t sp = (int32_t) x - back;
+				w->E[x] = sp >= (int32_t) a ? (uint16_t) sp : (uint16_t) (E_BYTE | w->H[(hb + (uint32_t) sp) & (WIDE_H - 1u)]);
+				x++;
+				left--;
 			}
-			const uint32_t dist = tok & 0xffffu;
-			if (dist <= x - a) {
-				const uint32_t sx = x - dist;
-				for (uint32_t j = 0; j < len; j++) w->E[x + j] = (uint16_t) (sx + j);
-			} else {
-				for (uint32_t j = 0; j < len; j++) {
-					const int32_t sp = (int32_t) (x + j) - (int32_t) dist;
-					w->E[x + j] = sp >= (int32_t) a ? (uint16_t) sp
-					                                : (uint16_t) (E_BYTE | w->H[(hb + (uint32_t) sp) & (WIDE_H - 1u)]);
+		}
+		const uint32_t maxn = __reduce_max_sync(JDB_FULL_MASK, myn);
+		uint32_t x = x0;
+		for (uint32_t i = 0; i < maxn; i++) {
+			const uint32_t tok = i < myn ? slots[i * 32u] : 0u;
+			const uint32_t len = tok >> 16;
+			unsigned lm = __ballot_sync(JDB_FULL_MASK, len > WIDE_LONG);
+			while (lm) {
+				const int from = __ffs(lm) - 1;
+				lm &= lm - 1;
+				const uint32_t x2 = __shfl_sync(JDB_FULL_MASK, x, from);
+				const uint32_t t2 = __shfl_sync(JDB_FULL_MASK, tok, from);
+				const uint32_t l2 = t2 >> 16;
+				const int32_t d2 = (int32_t) (t2 & 0xffffu);
+				for (uint32_t j = lane; j < l2; j += 32u) {
+					const int32_t sp = (int32_t) (x2 + j) - d2;
+					w->E[x2 + j] = sp >= (int32_t) a ? (uint16_t) sp : (uint16_t) (E_BYTE | w->H[(hb + (uint32_t) sp) & (WIDE_H - 1u)]);
 				}
 			}
-			x += len;
+			x += len ? len : (i < myn ? 1u : 0u);
 		}
 	}
 	__syncthreads();
+	WPROF(4);           /* expand */
 
 	/* ---- resolve ---- */
 	const uint32_t nquad = (a + nbytes + 3u) >> 2;
-	uint64_t* const E4 = (uint64_t*) w->E;
-	for (uint32_t it = 0; nbytes; it++) {
+	uint2* const E4 = (uint2*) w->E;
+	while (nbytes) {
 		bool more = false;
-		for (uint32_t q = gl; q < nquad; q += WIDE_LANES) {
-			uint64_t e4 = E4[q];
-			if ((e4 & 0x8000800080008000ull) == 0x8000800080008000ull) continue;
-#pragma unroll
-			for (uint32_t k = 0; k < 4; k++) {
-				const uint32_t e = (uint32_t) (e4 >> (16u * k)) & 0xffffu;
-				if (e & E_BYTE) continue;
-				const uint32_t f = w->E[e];
-				if (!(f & E_BYTE)) more = true;
-				e4 = (e4 & ~(0xffffull << (16u * k))) | ((uint64_t) f << (16u * k));
-			}
+		WCOUNT(10, 1);
+		for (uint32_t q0 = 0; q0 < nquad; q0 += WIDE_LANES, __syncwarp()) {
+			const uint32_t q = q0 + gl;
+			if (q >= nquad) continue;
+			uint2 e4 = E4[q];
+			if ((e4.x & e4.y & 0x80008000u) == 0x80008000u) continue;
+			/* (the four sources are loaded before any of them is looked at) */
+			const uint32_t e0 = e4.x & 0xffffu, e1 = e4.x >> 16, e2 = e4.y & 0xffffu, e3 = e4.y >> 16;
+			const uint32_t f0 = (e0 & E_BYTE) ? e0 : w->E[e0];
+			const uint32_t f1 = (e1 & E_BYTE) ? e1 : w->E[e1];
+			const uint32_t f2 = (e2 & E_BYTE) ? e2 : w->E[e2];
+			const uint32_t f3 = (e3 & E_BYTE) ? e3 : w->E[e3];
+			e4.x = f0 | (f1 << 16);
+			e4.y = f2 | (f3 << 16);
+			if ((e4.x & e4.y & 0x80008000u) != 0x80008000u) more = true;
 			E4[q] = e4;
 		}
-		if (__any_sync(JDB_FULL_MASK, more) && lane == 0) w->anyjump[it & 1] = 1;
-		__syncthreads();
-		const uint32_t again = w->anyjump[it & 1];
-		if (gl == 0) w->anyjump[(it + 1) & 1] = 0;
-		if (!again) break;
-		/* (the flag of sweep it + 1 was cleared before the barrier of sweep it - 1 ... it is
-		 * cleared here, after everybody's read of sweep it - 1's and before anybody's
-		 * write of sweep it + 1's, which lies behind the next barrier) */
-		__syncthreads();
+		if (!__syncthreads_or(more)) break;
 	}
-
+	WPROF(5);           /* resolve */
 	/* ---- write: target and mirror ---- */
 	{
 		uint8_t* const dal = dst + out - a;                       /* 4-byte aligned */
 		const uint32_t hal = rbase + (uint32_t) out - a;
-		for (uint32_t q = gl; q < nquad; q += WIDE_LANES) {
-			const uint64_t e4 = E4[q];
-			const uint32_t word = (uint32_t) (e4 & 0xffu) | ((uint32_t) (e4 >> 8) & 0xff00u) |
-			                      ((uint32_t) (e4 >> 16) & 0xff0000u) | ((uint32_t) (e4 >> 24) & 0xff000000u);
+		for (uint32_t q0 = 0; q0 < nquad; q0 += WIDE_LANES, __syncwarp()) {
+			const uint32_t q = q0 + gl;
+			if (q >= nquad) continue;
+			const uint2 e4 = E4[q];
+			const uint32_t word = __byte_perm(e4.x, e4.y, 0x6420);
 			const uint32_t x0 = 4u * q;
 			if (x0 >= a && x0 + 4u <= a + nbytes) {
 				*(uint32_t*) (dal + x0) = word;
@@ -981,6 +1181,10 @@ wide_round(const uint32_t* lit, const uint32_t* dtab, WideMem* w)
 		w->h_valid = 1;
 	}
 	__syncthreads();
+	WPROF(6);           /* write */
+	WCOUNT(8, 1);
+	WCOUNT(11, nbytes);
+	WCOUNT(7, v);
 }
 
 /*
@@ -989,8 +1193,11 @@ wide_round(const uint32_t* lit, const uint32_t* dtab, WideMem* w)
  */
 template <bool WIDE>
 static __device__ void
-inflate_stream(WarpMem* m, Stream& s, WideMem* w)
+inflate_stream(WarpMem* m_, Stream& s, WideMem* w_)
 {
+	/* (the master of a wide CTA is a lone warp on the critical path of its CTA: see jdb_pin_shared) */
+	WarpMem* const m = WIDE ? jdb_pin_shared(m_) : m_;
+	WideMem* const w = WIDE ? jdb_pin_shared(w_) : w_;
 	const unsigned lane = jdb_lane();
 	Bits b;
 	uint32_t phase = JDB_INF_HEADER;    /* where we are in the block structure */
@@ -1172,9 +1379,12 @@ inflate_stream(WarpMem* m, Stream& s, WideMem* w)
 			for (;;) {
 				/* ---- all lanes: keep the input of one lane-parallel round (or >= 3 KiBit) ahead
 				 * of `o` in the ring ---- */
-				const uint32_t ahead = 32u * S + 64u > 3072u ? 32u * S + 64u : 3072u;
+				/* (the master of a wide CTA needs its own ring for the step-by-step decoder and for the
+				 * way out only: wide rounds stage their input themselves) */
+				const bool go_wide = WIDE && !pend_len && !step_by_step && !wide_ev && endbit - o >= 2u * S + 64u;
+				const uint32_t ahead = WIDE ? 3072u : 32u * S + 64u > 3072u ? 32u * S + 64u : 3072u;
 				if (o >= filled) filled = o & ~1023u;
-				while (filled < o + ahead && filled < fill_limit) {
+				while (!go_wide && filled < o + ahead && filled < fill_limit) {
 					const uint32_t k = (filled >> 5) + lane;
 					uint32_t v = 0;
 					if (k < nwords) {
@@ -1211,7 +1421,7 @@ inflate_stream(WarpMem* m, Stream& s, WideMem* w)
 					pend_len = 0;
 				} else
 #ifndef PAR_OFF
-				if (WIDE && !step_by_step && endbit - o >= 2u * S + 64u) {
+				if (WIDE && go_wide) {
 					/* ---- the round on all warps of the CTA (wide_round): everything produced so
 					 * far goes to the target first, the round writes behind it ---- */
 					flush_ring(s, s.out, true);
@@ -1228,7 +1438,6 @@ inflate_stream(WarpMem* m, Stream& s, WideMem* w)
 						w->history = s.st ? s.st->history : (const uint8_t*) 0;
 						w->total_before = s.total_before;
 						w->hist_avail = s.hist_avail;
-						w->anyrun[0] = 0; w->anyrun[1] = 0;
 					}
 					__syncthreads();
 					wide_round(m->lit, m->dist, w);
@@ -1625,6 +1834,9 @@ inflate_wide_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ 
 		return;
 	}
 	if (lane == 0) { w->h_valid = 0; w->h_hi = 0; }
+#ifdef WIDE_PROF
+	if (lane == 0) { for (int k = 0; k < 12; k++) w->pt[k] = 0; for (int k = 0; k < 16; k++) { w->runs[k] = 0; w->pcyc[k] = 0; } w->t_last = clock64(); }
+#endif
 	__syncwarp();
 	const jdb_inflate_item it = items[idx];
 	Stream s;
@@ -1643,6 +1855,19 @@ inflate_wide_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ 
 	if (lane == 0) {
 		results[idx] = r;
 		w->cmd = 0;
+#ifdef WIDE_PROF
+		WPROF(0);
+		printf("wide: lanes decoding in pass k, per round:");
+		for (int k = 0; k < 13; k++) printf(" %.1f", (double) w->runs[k] / w->pt[8]);
+		printf("\n");
+		printf("wide: kcycles of pass k, per round:");
+		for (int k = 0; k < 12; k++) printf(" %.1f", (double) w->pcyc[k] / 1e3 / w->pt[8]);
+		printf("\n");
+		printf("wide: rounds %lld lanes/round %.1f passes/round %.2f sweeps/round %.2f bytes/round %.0f | kcycles/round: master %.1f stage %.1f decode %.1f chain %.1f expand %.1f resolve %.1f write %.1f\n",
+		       w->pt[8], (double) w->pt[7] / w->pt[8], (double) w->pt[9] / w->pt[8], (double) w->pt[10] / w->pt[8], (double) w->pt[11] / w->pt[8],
+		       w->pt[0] / 1e3 / w->pt[8], w->pt[1] / 1e3 / w->pt[8], w->pt[2] / 1e3 / w->pt[8], w->pt[3] / 1e3 / w->pt[8],
+		       w->pt[4] / 1e3 / w->pt[8], w->pt[5] / 1e3 / w->pt[8], w->pt[6] / 1e3 / w->pt[8]);
+#endif
 	}
 	__syncthreads();
 }

@@ -129,6 +129,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem, std::function<void()> body)
 		cta.alive = n;
 		cta.bar_arrived = 0;
 		cta.bar_gen = 0;
+		cta.or_flag = 0;
 		memset(cta.nb_arrived, 0, sizeof(cta.nb_arrived));
 		memset(cta.nb_gen, 0, sizeof(cta.nb_gen));
 		memset(cta.warps, 0, sizeof(cta.warps));

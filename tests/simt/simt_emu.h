@@ -73,6 +73,7 @@ struct Cta {
 	int      alive;
 	int      bar_arrived;
 	unsigned bar_gen;
+	int      or_flag;              /* __syncthreads_or */
 	int      nb_arrived[16];       /* named barriers (bar.sync id, count) */
 	unsigned nb_gen[16];
 	Warp     warps[32];
@@ -118,6 +119,18 @@ static inline void __syncthreads()
 		simt::yield();
 }
 
+static inline int __syncthreads_or(int pred)
+{
+	simt::Cta* c = simt::g_cta;
+	if (pred) c->or_flag = 1;
+	__syncthreads();
+	const int r = c->or_flag;
+	__syncthreads();
+	if (simt::g_cta->cur == 0 || simt::self().tid.x + simt::self().tid.y + simt::self().tid.z == 0) c->or_flag = 0;
+	__syncthreads();
+	return r;
+}
+
 /* bar.sync id, count: `count` threads of the CTA meet at named barrier `id` */
 static inline void simt_named_barrier(unsigned id, int count)
 {
@@ -136,6 +149,7 @@ static inline void __syncwarp(unsigned mask = 0xffffffffu) { simt::collective(ma
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 static inline void __nanosleep(unsigned) {}
+static inline long long clock64() { return 0; }
 
 static inline unsigned __ballot_sync(unsigned mask, int pred)
 {
