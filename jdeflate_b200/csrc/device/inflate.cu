@@ -756,6 +756,8 @@ lane_decode(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, ui
 #ifndef WIDE_S0
 #define WIDE_S0          160u
 #endif
+#define WIDE_SMIN         PQ_K       /* bits: a subsequence this short never runs out of token slots (a code has >= 1 bit) */
+#define WIDE_MIN_ROOM    2048u      /* target room below which a round of the whole CTA is not worth its barriers */
 #define E_BYTE           0x8000u
 #ifndef WIDE_LONG
 #define WIDE_LONG        24u        /* longer matches are expanded by all lanes of a warp */
@@ -980,7 +982,10 @@ wide_round(const uint32_t* lit_, const uint32_t* dtab_, WideMem* w_)
 			lane_decode_w(inbuf, lit, dtab, slots, r, run, st, lim, safe_end);
 			WCOUNT(9, 1);
 #ifdef WIDE_PROF
-			if (run) atomicAdd((unsigned long long*) &w->runs[pass < 15 ? pass : 15], 1ull);
+			{
+				const unsigned rm = __ballot_sync(JDB_FULL_MASK, run);      /* (one atomic per warp: 512 contended ones cost more than the pass) */
+				if (lane == 0 && rm) atomicAdd((unsigned long long*) &w->runs[pass < 15 ? pass : 15], (unsigned long long) __popc(rm));
+			}
 #endif
 			if (lane == 31) { w->wend[wp] = r.end; w->wflag[wp] = r.flag; }
 			__syncthreads();
@@ -1059,7 +1064,7 @@ wide_round(const uint32_t* lit_, const uint32_t* dtab_, WideMem* w_)
 		 * again while both stay half empty */
 		uint32_t full = 0, maxn = 0, ns = S;
 		for (uint32_t k = 0; k < WIDE_WARPS; k++) { full |= w->wfull[k]; if (w->wmaxn[k] > maxn) maxn = w->wmaxn[k]; }
-		if (full || capped) ns = S >= PAR_SMIN + 32u ? S - 32u : PAR_SMIN;
+		if (full || capped) ns = S >= WIDE_SMIN + 32u ? S - 32u : WIDE_SMIN;
 		else if (maxn <= 3u * PQ_K / 4u && S < PAR_SMAX && v >= 32u &&
 		         (uint64_t) nbytes * WIDE_LANES * (S + 32u) < (uint64_t) (WIDE_CAP - WIDE_CAP / 8u) * v * S) ns = S + 32u;
 		w->newS = ns;
@@ -1096,10 +1101,17 @@ wide_round(const uint32_t* lit_, const uint32_t* dtab_, WideMem* w_)
 					left = len;
 					back = (int32_t) (tok & 0xffffu);
 				}
+				/* up to four entries of the match in hand per trip */
+				const uint32_t k = left < 4u ? left : 4u;
 				const int32_t sp = (int32_t) x - back;
-				w->E[x] = sp >= (int32_t) a ? (uint16_t) sp : (uint16_t) (E_BYTE | w->H[(hb + (uint32_t) sp) & (WIDE_H - 1u)]);
-				x++;
-				left--;
+#pragma unroll
+				for (uint32_t j = 0; j < 4u; j++)
+					if (j < k)
+						w->E[x + j] = sp + (int32_t) j >= (int32_t) a
+						            ? (uint16_t) (sp + (int32_t) j)
+						            : (uint16_t) (E_BYTE | w->H[(hb + (uint32_t) sp + j) & (WIDE_H - 1u)]);
+				x += k;
+				left -= k;
 			}
 		}
 		const uint32_t maxn = __reduce_max_sync(JDB_FULL_MASK, myn);
@@ -1381,7 +1393,8 @@ inflate_stream(WarpMem* m_, Stream& s, WideMem* w_)
 				 * of `o` in the ring ---- */
 				/* (the master of a wide CTA needs its own ring for the step-by-step decoder and for the
 				 * way out only: wide rounds stage their input themselves) */
-				const bool go_wide = WIDE && !pend_len && !step_by_step && !wide_ev && endbit - o >= 2u * S + 64u;
+				const bool go_wide = WIDE && !pend_len && !step_by_step && !wide_ev && endbit - o >= 2u * S + 64u &&
+				                     s.dst_cap - s.out >= WIDE_MIN_ROOM;      /* the tail of a target window: step by step */
 				const uint32_t ahead = WIDE ? 3072u : 32u * S + 64u > 3072u ? 32u * S + 64u : 3072u;
 				if (o >= filled) filled = o & ~1023u;
 				while (!go_wide && filled < o + ahead && filled < fill_limit) {

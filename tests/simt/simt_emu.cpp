@@ -114,8 +114,10 @@ void run_grid(dim3 grid, dim3 block, size_t smem, std::function<void()> body)
 	cta.bdim = block;
 	cta.gdim = grid;
 	cta.body = body;
-	std::vector<char*> stacks(n);
-	for (int i = 0; i < n; i++) stacks[i] = (char*) malloc(STACK_BYTES);
+	/* fiber stacks are kept between launches (a test may launch a 512-thread CTA tens of
+	 * thousands of times); nested launches do not happen */
+	static std::vector<char*> stacks;
+	while ((int) stacks.size() < n) stacks.push_back((char*) malloc(STACK_BYTES));
 	unsigned char* dsmem = (unsigned char*) aligned_alloc(128, ((smem + 127) / 128 + 1) * 128);
 	Cta* saved_cta = g_cta;
 	unsigned char* saved_ds = g_dsmem;
@@ -159,7 +161,6 @@ void run_grid(dim3 grid, dim3 block, size_t smem, std::function<void()> body)
 
 	g_cta = saved_cta;
 	g_dsmem = saved_ds;
-	for (int i = 0; i < n; i++) free(stacks[i]);
 	free(dsmem);
 }
 

@@ -275,10 +275,17 @@ def test_target_windows_cut_lane_parallel_rounds(lib, corpus):
     a match cut by the window end is continued by the next call."""
     d = corpus.fill(4, 40000, offset=11) + bytes(5000) + corpus.fill(0, 20000, offset=3)
     z = zlib_raw(d, 6)
-    for window in (1, 2, 3, 5, 17, 255, 258, 259, 1000, 4095, 4096, 4097, 33000):
+    for window in (255, 258, 259, 1000, 4095, 4096, 4097, 33000):
         st, err, out, used = lib.inflate_bytes(z, len(d), window=window)
         assert (st, err, used) == (api.OK, 0, len(z)), window
         assert out == d, window
+    # the smallest windows on a shorter stream (one launch per window)
+    ds = d[36000:48000]
+    zs = zlib_raw(ds, 6)
+    for window in (1, 2, 3, 5, 17):
+        st, err, out, used = lib.inflate_bytes(zs, len(ds), window=window)
+        assert (st, err, used) == (api.OK, 0, len(zs)), window
+        assert out == ds, window
     # exact fit, one byte short, and a target that ends inside a long match
     for cap in (len(d), len(d) - 1, 40000 + 2500):
         st, err, out, used = lib.inflate_bytes(z, cap)
@@ -323,3 +330,111 @@ def test_batch_records_at_every_alignment(lib, corpus):
     outs, res = lib.inflate_batch_bytes(streams, [len(r) for r in recs], fmt=api.JDB200_RAW)
     for i, (r, o, q) in enumerate(zip(recs, outs, res)):
         assert (q.status, q.error) == (api.OK, 0) and o == r, i
+
+
+# ---- one stream on a whole CTA (inflate_wide_kernel: the sequential path of inflator_inflate) ----
+
+def _mixed_stream(corpus, n, level=6):
+    """Text, binary, logs, random and a run of zeros in one stream: dynamic, fixed and stored blocks,
+    short and 258-byte matches, distances up to the window."""
+    import numpy as np
+    parts, k = [], 0
+    while sum(map(len, parts)) < n:
+        kind = k % 6
+        m = 30000 + 7919 * (k % 7)
+        if kind == 5:
+            parts.append(bytes(m // 3) if k % 2 else np.random.RandomState(k).randint(0, 256, m // 4, dtype=np.uint8).tobytes())
+        else:
+            parts.append(corpus.fill(kind % 5, m, offset=k * 100003))
+        k += 1
+    d = b"".join(parts)[:n]
+    return d, zlib_raw(d, level)
+
+
+def test_wide_rounds_long_stream(lib, oracle, corpus):
+    """A third-party stream long enough for full rounds of 512 lanes, in one call and in windows that
+    cut rounds short at every kind of place (target room, source end), against zlib's bytes and the
+    oracle's status / accounting."""
+    d, z = _mixed_stream(corpus, 1_300_000)
+    st, err, out, used = lib.inflate_bytes(z + b"\x01\x02\x03", len(d) + 5)
+    assert (st, err, used) == (api.OK, 0, len(z)) and out == d
+    want = oracle.inflate(z + b"\x01\x02\x03", len(d) + 5)
+    assert (want[0], want[1], want[3]) == (st, err, used)
+    for feed, window in ((None, 70001), (33333, 65536), (4099, 1 << 20), (100000, 9973)):
+        st, err, out, used = lib.inflate_bytes(z, len(d), window=window, feed=feed)
+        assert (st, err, used) == (api.OK, 0, len(z)), (feed, window)
+        assert out == d, (feed, window)
+    # the target ends inside the stream: exactly cap bytes, TGTEXHSTD
+    for cap in (1, 4097, 65537, 700001):
+        st, err, out, _ = lib.inflate_bytes(z, cap)
+        assert st == api.TGTEXHSTD and out == d[:cap], cap
+
+
+def test_wide_rounds_levels_and_kinds(lib, corpus):
+    for kind in range(5):
+        d = corpus.fill(kind, 400_000, offset=kind * 31)
+        for lvl in (1, 9):
+            z = zlib_raw(d, lvl)
+            st, err, out, used = lib.inflate_bytes(z, len(d))
+            assert (st, err, used) == (api.OK, 0, len(z)) and out == d, (kind, lvl)
+
+
+def test_wide_rounds_history_and_dictionary(lib, corpus):
+    """Distances that reach into earlier calls' output (the history ring of the device state) and
+    into a preset dictionary: the wide rounds mirror the last 32 KiB in shared memory."""
+    dct = corpus.fill(0, 32768, offset=11)
+    d = dct[1000:30000] + corpus.fill(0, 300_000, offset=424242) + dct[:20000]
+    co = zlib.compressobj(9, zlib.DEFLATED, -15, zdict=dct)
+    z = co.compress(d) + co.flush()
+    for feed, window in ((None, None), (5000, 20011), (77777, 300)):
+        s = lib.inflator()
+        try:
+            s.setdctnr(dct)
+            st, err, out, used = s.run(z, len(d), window=window, feed=feed)
+            assert (st, err, used) == (api.OK, 0, len(z)) and out == d, (feed, window)
+        finally:
+            s.close()
+
+
+def test_wide_rounds_corruption_parity(lib, oracle, corpus):
+    """Damage deep inside a long stream: status, error and the bytes in front of it as the oracle has them."""
+    rnd = random.Random(4242)
+    d, z = _mixed_stream(corpus, 400_000)
+    for _ in range(25):
+        m = bytearray(z)
+        for _ in range(rnd.randint(1, 2)):
+            m[rnd.randrange(len(m) // 3, len(m))] ^= 1 << rnd.randrange(8)
+        want = oracle.inflate(bytes(m), len(d) + 100)
+        got = lib.inflate_bytes(bytes(m), len(d) + 100)
+        assert (got[0], got[1]) == (want[0], want[1])
+        if want[0] == api.OK:
+            assert got[2] == want[2] and got[3] == want[3]
+        else:
+            assert got[2] == want[2][: len(got[2])] or want[2] == got[2][: len(want[2])]
+
+
+@pytest.mark.gpu
+def test_wide_and_narrow_decoders_agree_on_device_targets(jd, corpus):
+    """Device buffers at every target alignment: the CTA-wide decoder writes aligned words from its entry
+    array, the one-warp decoder from its ring -- same bytes, same accounting."""
+    import os
+    import torch
+    d, z = _mixed_stream(corpus, 3_000_000)
+    src = torch.frombuffer(bytearray(z), dtype=torch.uint8).cuda()
+    want = torch.frombuffer(bytearray(d), dtype=torch.uint8).cuda()
+    for narrow in ("0", "1"):
+        os.environ["JDB200_INFLATE_NARROW"] = narrow
+        try:
+            for off in (0, 1, 2, 3):
+                back = torch.zeros(len(d) + 8, dtype=torch.uint8, device="cuda")
+                s = jd.inflator()
+                try:
+                    s.setsrc(src.data_ptr(), len(z))
+                    s.settgt(back.data_ptr() + off, len(d))
+                    assert s.inflate(1) == api.OK and s.tgtend() == len(d) and s.srcend() == len(z)
+                finally:
+                    s.close()
+                assert torch.equal(back[off:off + len(d)], want), (narrow, off)
+                assert int(back[:off].sum()) == 0 and int(back[off + len(d):].sum()) == 0
+        finally:
+            os.environ.pop("JDB200_INFLATE_NARROW", None)
