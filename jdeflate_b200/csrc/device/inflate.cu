@@ -428,6 +428,14 @@ parse_block_header(BuildMem* bm, uint32_t* lit, uint32_t* dist, Bits& gb_, uint3
 				uint32_t i = 0;
 				const uint32_t n = hlit + hdist;
 				while (i < n) {
+					/* (four bytes of the staged header at a time; a refill per byte is a dependent
+					 * load in front of every code length) */
+					if (b.bc <= 32 && b.p + 4 <= b.end) {
+						const uint32_t v = (uint32_t) b.p[0] | ((uint32_t) b.p[1] << 8) | ((uint32_t) b.p[2] << 16) | ((uint32_t) b.p[3] << 24);
+						b.bb |= (uint64_t) v << b.bc;
+						b.p += 4;
+						b.bc += 32;
+					}
 					bits_need(b, 7);
 					uint32_t e = lit[(uint32_t) b.bb & 127u];
 					uint32_t nb = e & 15u;
@@ -757,6 +765,7 @@ lane_decode(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, ui
 #define WIDE_S0          160u
 #endif
 #define WIDE_SMIN         PQ_K       /* bits: a subsequence this short never runs out of token slots (a code has >= 1 bit) */
+#define WIDE_COPY_MIN     4096u      /* stored bytes from which the whole CTA copies */
 #define WIDE_MIN_ROOM    2048u      /* target room below which a round of the whole CTA is not worth its barriers */
 #define E_BYTE           0x8000u
 #ifndef WIDE_LONG
@@ -779,6 +788,7 @@ lane_decode_w(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, 
 {
 	uint32_t pos = start, n = 0, bytes = 0, flag = PF_OK;
 	int32_t need = 0;
+	uint32_t* slot = slots;
 	uint32_t cur = pos >> 5;
 	uint32_t w0 = inbuf[cur & (INW - 1u)], w1 = inbuf[(cur + 1u) & (INW - 1u)], w2 = inbuf[(cur + 2u) & (INW - 1u)];
 	bool act = run && pos < limit;
@@ -831,7 +841,8 @@ lane_decode_w(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, 
 					act = false;
 				}
 				if (act) {
-					slots[n * 32u] = tok;
+					*slot = tok;
+					slot += 32;
 					n++;
 					act = pos < limit;
 				}
@@ -873,7 +884,10 @@ lane_lead_in(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, u
 
 struct WideMem {
 	/* command block: written by the master before the command barrier */
-	uint32_t cmd;                   /* 0: leave, 1: round */
+	uint32_t cmd;                   /* 0: leave, 1: round, 2: copy (stored block) */
+	const uint8_t* cp_src;          /* copy: source, target, bytes */
+	uint8_t* cp_dst;
+	uint32_t cp_n;
 	uint32_t o, S, endbit, nwords, pre, c, prefix_word;
 	int32_t  delta;
 	uint32_t room, reach;
@@ -922,8 +936,8 @@ wide_round(const uint32_t* lit_, const uint32_t* dtab_, WideMem* w_)
 	const unsigned lane = jdb_lane(), wp = jdb_warp(), gl = threadIdx.x;
 	const uint32_t o = w->o, S = w->S, endbit = w->endbit;
 	const uint32_t safe_end = endbit - 64u;
-	uint32_t* const inbuf = w->inbuf[wp];
-	uint32_t* const slots = w->slots[wp] + lane;
+	uint32_t* const inbuf = jdb_pin_shared(w->inbuf[wp]);        /* (in registers, not rebuilt from the warp number in the decode loop) */
+	uint32_t* const slots = jdb_pin_shared(w->slots[wp] + lane);
 	uint8_t* const dst = w->dst;
 	const uint64_t out = w->out;
 	const uint32_t rbase = (uint32_t) (uintptr_t) dst;
@@ -1199,6 +1213,35 @@ wide_round(const uint32_t* lit_, const uint32_t* dtab_, WideMem* w_)
 	WCOUNT(7, v);
 }
 
+/* all threads of the CTA: the bytes of a stored block, source to target (any alignments): target-aligned
+ * 32-bit words, each from the two aligned source words that hold its bytes */
+static __device__ __noinline__ void
+wide_copy(WideMem* w_)
+{
+	WideMem* const w = jdb_pin_shared(w_);
+	const unsigned gl = threadIdx.x;
+	uint8_t* const d = w->cp_dst;
+	const uint8_t* const p = w->cp_src;
+	const uint32_t n = w->cp_n;
+	uint32_t head = (4u - (uint32_t) ((uintptr_t) d & 3u)) & 3u;
+	if (head > n) head = n;
+	const uint32_t nw = (n - head) >> 2;
+	const uint32_t tail0 = head + 4u * nw;
+	if (gl < head) d[gl] = __ldg(p + gl);
+	if (tail0 + gl < n) d[tail0 + gl] = __ldg(p + tail0 + gl);
+	const uint8_t* const ps = p + head;
+	const uint32_t* const pw = (const uint32_t*) ((uintptr_t) ps & ~(uintptr_t) 3);
+	const uint32_t sh = 8u * (uint32_t) ((uintptr_t) ps & 3u);
+	uint32_t* const dw = (uint32_t*) (d + head);
+#pragma unroll 4
+	for (uint32_t i = gl; i < nw; i += WIDE_LANES) {
+		const uint32_t lo = __ldg(pw + i);
+		const uint32_t hi = sh ? __ldg(pw + i + 1) : 0u;      /* never past the word of the last byte */
+		dw[i] = __funnelshift_r(lo, hi, sh);
+	}
+	__syncthreads();
+}
+
 /*
  * Decode one stream (or one call's worth of a streaming decode).
  * Called by all 32 lanes of a warp with identical arguments.
@@ -1292,6 +1335,21 @@ inflate_stream(WarpMem* m_, Stream& s, WideMem* w_)
 			uint64_t srcleft = s.src_len - pos, dstleft = s.dst_cap - s.out;
 			if (n > srcleft) n = srcleft;
 			if (n > dstleft) n = dstleft;
+			if (WIDE && n >= WIDE_COPY_MIN) {
+				/* a block worth the barriers: copied by all warps; like the bytes of a wide round,
+				 * these reach later matches through L2, not through the master's ring */
+				flush_ring(s, s.out, true);
+				if (lane == 0) {
+					w->cmd = 2;
+					w->cp_src = s.src + pos;
+					w->cp_dst = s.dst + s.out;
+					w->cp_n = (uint32_t) n;
+				}
+				__syncthreads();
+				wide_copy(w);
+				s.flushed = s.out + n;
+				s.ring_lo = (int64_t) (s.out + n);
+			} else
 			if (!s.count_only) {
 				/* straight to the target, and into the ring for the matches of later blocks */
 				flush_ring(s, s.out, true);
@@ -1841,8 +1899,10 @@ inflate_wide_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ 
 	if (jdb_warp() != 0) {
 		for (;;) {
 			__syncthreads();
-			if (w->cmd == 0) break;
-			wide_round(m->lit, m->dist, w);
+			const uint32_t cmd = w->cmd;
+			if (cmd == 0) break;
+			if (cmd == 2) wide_copy(w);
+			else wide_round(m->lit, m->dist, w);
 		}
 		return;
 	}
