@@ -773,18 +773,34 @@ lane_decode(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, ui
 #endif
 
 /*
+ * Flattened tables of the wide rounds (built by all threads of the CTA whenever the master has
+ * new block tables, wide_flatten): one look-up, WIDE_LROOT / WIDE_DROOT bits wide, answers every
+ * code of up to that many bits -- a literal or a length base in the entry format of the two-level
+ * tables -- and everything else (longer codes, end of block, codes that do not exist, reserved
+ * symbols) is W_SPECIAL: the two-level tables and the code that judges them take over.
+ */
+#define WIDE_LROOT       11
+#define WIDE_DROOT       10
+#define W_SPECIAL        0x8000u
+#define W_MATCH          0x0100u    /* = T_BASE << 8 */
+
+/*
  * lane_decode for the wide rounds, where the latency of ONE warp's pass is what a round waits
- * for.  Called by all lanes of a warp (`run`: this lane takes part).  Two differences to
- * lane_decode: the three input words around the position stay in registers (a peek is one funnel
- * shift, the ring is read when the position enters the next word); and the loop is closed by a
- * vote, one symbol per trip for every lane still at work -- a loop that lanes leave one by one
- * through breaks is compiled without a reconvergence point behind the literal / match branch
- * by some builds, after which the lanes of a warp run its trips in ever smaller groups, one
- * group after the other (measured: 3x the time of a pass).
+ * for.  Called by all lanes of a warp (`run`: this lane takes part).  Differences to lane_decode:
+ *  - the three input words around the position stay in registers (a peek is one funnel shift,
+ *    the ring is read when the position enters the next word);
+ *  - a symbol is straight-line code for literals and matches alike: one look-up in the flattened
+ *    lit/len table, the distance look-up done whether or not it is needed, selects instead of
+ *    branches -- a warp whose lanes hold literals and matches runs ONE path per trip, not both one
+ *    after the other (measured: the dependent instructions of a trip, not the memory, are what a
+ *    pass costs);
+ *  - the loop is closed by a vote, one symbol per trip for every lane still at work: a loop
+ *    that lanes leave one by one through breaks was compiled without a reconvergence point by some
+ *    builds, after which the lanes of a warp ran its trips in ever smaller groups (3x the time).
  */
 static __device__ __forceinline__ void
-lane_decode_w(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, uint32_t* slots, LaneRun& r,
-              bool run, uint32_t start, uint32_t limit, uint32_t safe_end)
+lane_decode_w(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, const uint32_t* wlit, const uint32_t* wdist,
+              uint32_t* slots, LaneRun& r, bool run, uint32_t start, uint32_t limit, uint32_t safe_end)
 {
 	uint32_t pos = start, n = 0, bytes = 0, flag = PF_OK;
 	int32_t need = 0;
@@ -806,39 +822,58 @@ lane_decode_w(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, 
 					cur = i;
 				}
 				const uint32_t bits = __funnelshift_r(w0, w1, pos);
-				const uint32_t e = lookup32(lit, bits, LIT_ROOT);
-				const uint32_t nb = e & 15u;
-				const uint32_t type = (e >> 8) & 3u;
-				uint32_t tok = 0;
-				if (nb == 0) {
-					flag = PF_ANOM;
-					act = false;
-				} else if (type == T_LIT) {
-					tok = e >> 16;
-					pos += nb;
-					bytes += 1;
-				} else if (type == T_BASE) {
-					const uint32_t lxb = (e >> 4) & 15u;
-					const uint32_t len = (e >> 16) + ((bits >> nb) & ((1u << lxb) - 1u));
-					const uint32_t o2 = pos + nb + lxb;          /* in this word or the next */
-					const uint32_t bits2 = (o2 >> 5) == cur ? __funnelshift_r(w0, w1, o2) : __funnelshift_r(w1, w2, o2);
-					const uint32_t d = lookup32(dtab, bits2, DIST_ROOT);
-					const uint32_t dnb = d & 15u, dxb = (d >> 4) & 15u;
-					if ((e >> 16) == 0 || dnb == 0 || (d >> 16) == 0) {
+				const uint32_t e = wlit[bits & ((1u << WIDE_LROOT) - 1u)];
+				const uint32_t nb = e & 15u, lxb = (e >> 4) & 15u;
+				const uint32_t val = (e >> 16) + ((bits >> nb) & ((1u << lxb) - 1u));      /* the literal (lxb = 0), or the length */
+				const uint32_t o2 = pos + nb + lxb;                                        /* in this word or the next */
+				const uint32_t bits2 = (o2 >> 5) == cur ? __funnelshift_r(w0, w1, o2) : __funnelshift_r(w1, w2, o2);
+				const uint32_t d = wdist[bits2 & ((1u << WIDE_DROOT) - 1u)];
+				const bool m = (e & W_MATCH) != 0;
+				uint32_t tok;
+				if ((e | (m ? d : 0u)) & W_SPECIAL) {
+					/* ---- the two-level tables decide (lane_decode's body) ---- */
+					const uint32_t e1 = lookup32(lit, bits, LIT_ROOT);
+					const uint32_t nb1 = e1 & 15u;
+					const uint32_t type = (e1 >> 8) & 3u;
+					tok = 0;
+					if (nb1 == 0) {
 						flag = PF_ANOM;
 						act = false;
+					} else if (type == T_LIT) {
+						tok = e1 >> 16;
+						pos += nb1;
+						bytes += 1;
+					} else if (type == T_BASE) {
+						const uint32_t lxb1 = (e1 >> 4) & 15u;
+						const uint32_t len = (e1 >> 16) + ((bits >> nb1) & ((1u << lxb1) - 1u));
+						const uint32_t o3 = pos + nb1 + lxb1;
+						const uint32_t bits3 = (o3 >> 5) == cur ? __funnelshift_r(w0, w1, o3) : __funnelshift_r(w1, w2, o3);
+						const uint32_t d1 = lookup32(dtab, bits3, DIST_ROOT);
+						const uint32_t dnb = d1 & 15u, dxb = (d1 >> 4) & 15u;
+						if ((e1 >> 16) == 0 || dnb == 0 || (d1 >> 16) == 0) {
+							flag = PF_ANOM;
+							act = false;
+						} else {
+							const uint32_t dist = (d1 >> 16) + ((bits3 >> dnb) & ((1u << dxb) - 1u));
+							const int32_t nd = (int32_t) dist - (int32_t) bytes;
+							if (nd > need) need = nd;
+							tok = (len << 16) | dist;
+							pos = o3 + dnb + dxb;
+							bytes += len;
+						}
 					} else {
-						const uint32_t dist = (d >> 16) + ((bits2 >> dnb) & ((1u << dxb) - 1u));
-						const int32_t nd = (int32_t) dist - (int32_t) bytes;
-						if (nd > need) need = nd;
-						tok = (len << 16) | dist;
-						pos = o2 + dnb + dxb;
-						bytes += len;
+						pos += nb1;
+						flag = PF_EOB;
+						act = false;
 					}
 				} else {
-					pos += nb;
-					flag = PF_EOB;
-					act = false;
+					const uint32_t dnb = d & 15u, dxb = (d >> 4) & 15u;
+					const uint32_t dist = (d >> 16) + ((bits2 >> dnb) & ((1u << dxb) - 1u));
+					const int32_t nd = m ? (int32_t) dist - (int32_t) bytes : 0;
+					if (nd > need) need = nd;
+					tok = m ? (val << 16) | dist : val;
+					pos = m ? o2 + dnb + dxb : o2;
+					bytes += m ? val : 1u;
 				}
 				if (act) {
 					*slot = tok;
@@ -905,6 +940,9 @@ struct WideMem {
 	/* scratch */
 	uint32_t wend[WIDE_WARPS], wflag[WIDE_WARPS], wbrk[WIDE_WARPS], wsb[WIDE_WARPS], wsn[WIDE_WARPS];
 	uint32_t whard[WIDE_WARPS], wcap[WIDE_WARPS], wfull[WIDE_WARPS], wmaxn[WIDE_WARPS];
+	uint32_t tables_new;            /* the master has new block tables: flatten them first */
+	uint32_t wlit[1u << WIDE_LROOT];
+	uint32_t wdist[1u << WIDE_DROOT];
 	uint32_t inbuf[WIDE_WARPS][INW];
 	uint32_t slots[WIDE_WARPS][PQ_K * 32u];
 	__align__(8) uint16_t E[WIDE_E];
@@ -943,6 +981,27 @@ wide_round(const uint32_t* lit_, const uint32_t* dtab_, WideMem* w_)
 	const uint32_t rbase = (uint32_t) (uintptr_t) dst;
 	const uint32_t a = (uint32_t) ((uintptr_t) (dst + out) & 3u);       /* E-index of the round's first byte */
 	WPROF(0);           /* master between rounds */
+
+	/* ---- new block tables: flatten them (every thread a few entries; the two-level look-up with the
+	 * unknown upper bits zero is the answer for all of them when the code it finds is short enough) ---- */
+	if (w->tables_new) {
+		for (uint32_t i = gl; i < (1u << WIDE_LROOT); i += WIDE_LANES) {
+			const uint32_t e = lookup32(lit, i, LIT_ROOT);
+			const uint32_t nb = e & 15u, type = (e >> 8) & 3u;
+			const bool plain = nb != 0 && nb <= WIDE_LROOT && (type == T_LIT || (type == T_BASE && (e >> 16) != 0));
+			w->wlit[i] = plain ? e : W_SPECIAL;
+		}
+		for (uint32_t i = gl; i < (1u << WIDE_DROOT); i += WIDE_LANES) {
+			const uint32_t d = lookup32(dtab, i, DIST_ROOT);
+			const uint32_t nb = d & 15u;
+			const bool plain = nb != 0 && nb <= WIDE_DROOT && ((d >> 8) & 3u) == T_BASE && (d >> 16) != 0;
+			w->wdist[i] = plain ? d : W_SPECIAL;
+		}
+		__syncthreads();
+		if (gl == 0) w->tables_new = 0;
+	}
+	const uint32_t* const wlit = w->wlit;
+	const uint32_t* const wdist = w->wdist;
 
 	/* ---- the history mirror: whatever was produced since the last round (step-by-step
 	 * batches, stored blocks; everything, on the first round of a call) comes from L2 ---- */
@@ -993,7 +1052,7 @@ wide_round(const uint32_t* lit_, const uint32_t* dtab_, WideMem* w_)
 #ifdef WIDE_PROF
 			if (gl == 0) { const long long t_ = clock64(); if (pass) w->pcyc[pass < 16 ? pass - 1 : 15] += t_ - w->t_pass; w->t_pass = t_; }
 #endif
-			lane_decode_w(inbuf, lit, dtab, slots, r, run, st, lim, safe_end);
+			lane_decode_w(inbuf, lit, dtab, wlit, wdist, slots, r, run, st, lim, safe_end);
 			WCOUNT(9, 1);
 #ifdef WIDE_PROF
 			{
@@ -1424,6 +1483,7 @@ inflate_stream(WarpMem* m_, Stream& s, WideMem* w_)
 			 * logic, no 64-bit arithmetic, identical on all lanes (the lit/len and
 			 * distance look-ups are shared-memory broadcasts).  Up to 7 bits left in
 			 * the byte reader become a virtual byte in front of the window. */
+			if (WIDE && lane == 0) w->tables_new = 1;       /* (a new block, or the block in progress of an earlier call) */
 			b.p -= b.bc >> 3;
 			b.bc &= 7u;
 			b.bb &= (1ull << b.bc) - 1ull;
