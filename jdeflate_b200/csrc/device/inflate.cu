@@ -1,5 +1,6 @@
 /*
- * inflate.cu -- table driven DEFLATE decoder for sm_100a, one warp per stream.
+ * inflate.cu -- table driven DEFLATE decoder for sm_100a: one warp per stream of a batch,
+ * one thread block for a stream on its own.
  *
  * Replaces the reference's serial decoder: buildtable (src/inflator.c:380-568),
  * decodednmc/readlengths (:1029-1190), decodestrd (:930-1019), the hot loop
@@ -9,22 +10,22 @@
  * Work decomposition
  *   A DEFLATE stream is bit-serial, so parallelism comes from many streams
  *   (BASELINE config 3: 1 M independent records; our own output: independent
- *   chunks).  Each warp owns one stream at a time and pulls the next stream
- *   index from a global counter (dynamic load balance for 4-64 KiB records).
+ *   chunks).  inflate_batch_kernel: each warp owns one stream at a time and pulls
+ *   the next stream index from a global counter (dynamic load balance for 4-64 KiB
+ *   records).  inflate_wide_kernel: ONE stream that cannot be split (anybody's
+ *   zlib / gzip output) gets a CTA of 16 warps (see "one stream on a whole CTA").
  *
- *   Per warp, in shared memory: the two-level lookup tables (lit/len root
- *   10 bits, distance root 8 bits -- the reference's LROOTBITS/DROOTBITS,
- *   src/inflator.c:30-32), built warp-cooperatively per block, and a 32-entry
- *   symbol queue.  Lane 0 runs the bit-serial Huffman decode and fills the
- *   queue; then all 32 lanes turn the queue into bytes: a warp prefix sum
- *   gives every symbol its output offset, literals and short far matches are
- *   written by their own lane, long matches and matches that read bytes
- *   produced inside the same batch are copied warp-cooperatively in order.
- *   Output bytes are read back with ld.global.cg (L2) because they were
- *   written by other lanes of the warp.
+ *   Per warp, in shared memory: the two-level lookup tables (lit/len root 9 bits,
+ *   distance root 8 bits; the reference uses 10 / 8, src/inflator.c:30-32), built
+ *   warp-cooperatively per block, a 1 KiB ring of staged input and a 4 KiB ring of
+ *   the newest output.  The symbol loop is lane-parallel: every lane decodes its
+ *   own subsequence of the bit window, speculatively, and the chain of lanes whose
+ *   start is their predecessor's end is the decoded sequence (par_round); anything
+ *   a round does not judge goes through the step-by-step decoder, which owns every
+ *   status and error decision.  Tokens become bytes 32 at a time (emit_queue).
  *
  *   Algorithmic traffic: C compressed bytes read + N bytes written per stream
- *   (match sources are re-read from L2).
+ *   (match sources older than the ring are re-read from L2).
  *
  * Error model: the INFLT_* codes of jdeflate/inflator.h with the acceptance
  * rules of the reference (see oracle/jd_oracle.c for the restatement); the two
