@@ -38,7 +38,7 @@ extern "C" int jdb_pack_blocks(const uint8_t*, const uint32_t*, const uint32_t*,
 static size_t align256(size_t v) { return (v + 255) & ~(size_t) 255; }
 
 struct WorkLayout {
-	size_t prev, tok, seg_ntok, seg_hist, blocks, chunks, total, out, out_cap, bytes;
+	size_t prev, heads, tok, seg_ntok, seg_hist, blocks, chunks, total, out, out_cap, bytes;
 	uint32_t nseg, nchunks, bpc, nblocks;
 };
 
@@ -57,6 +57,7 @@ static int plan(uint64_t n, const jdb_deflate_cfg* cfg, WorkLayout* L)
 	const size_t npad = (size_t) (nseg ? nseg : 1) * SEG + 64;
 	size_t off = 0;
 	L->prev = off;      off += align256(npad * 2);
+	L->heads = off;     off += align256(jdb_lz_chain_heads_bytes(n, cfg->chunk_bytes));
 	L->tok = off;       off += align256(npad * 4);
 	L->seg_ntok = off;  off += align256(((size_t) nchunks * spc + 16) * 4);
 	L->seg_hist = off;  off += align256(((size_t) nchunks * spc + 1) * NSYM * 4);
@@ -99,6 +100,7 @@ extern "C" int jdb_deflate_run(const uint8_t* in, uint64_t n, const jdb_deflate_
 	if (r != JDB_OK) return r;
 	uint8_t* w = (uint8_t*) work;
 	uint16_t* prev = (uint16_t*) (w + L.prev);
+	uint16_t* heads = (uint16_t*) (w + L.heads);
 	uint32_t* tok = (uint32_t*) (w + L.tok);
 	uint32_t* seg_ntok = (uint32_t*) (w + L.seg_ntok);
 	uint32_t* seg_hist = (uint32_t*) (w + L.seg_hist);
@@ -121,12 +123,14 @@ extern "C" int jdb_deflate_run(const uint8_t* in, uint64_t n, const jdb_deflate_
 		 * sub-ranges that each replay 32 KiB of history first */
 		uint32_t range = cfg->chain_range;
 		if (range == 0) {
-			const uint64_t want = (uint64_t) jdb_rt_sm_count() * 3 * 4;
+			/* (no range replays history any more -- chain_fix_kernel -- so shorter ranges cost
+			 * nothing but their head table: six resident CTAs per SM, four waves) */
+			const uint64_t want = (uint64_t) jdb_rt_sm_count() * 6 * 4;
 			range = cfg->chunk_bytes;
 			while (range > 65536 && (range & 1) == 0 && (range / 2) % SEG == 0 && (n + range - 1) / range < want) range /= 2;
 		}
 		if (range > cfg->chunk_bytes || cfg->chunk_bytes % range || range % SEG) range = cfg->chunk_bytes;
-		r = jdb_lz_chain(in, n, cfg->chunk_bytes, range, cfg->chunk_len, prev, s);
+		r = jdb_lz_chain(in, n, cfg->chunk_bytes, range, cfg->chunk_len, prev, range >= 65536 ? heads : (uint16_t*) 0, s);   /* (the scratch is sized for ranges of 64 KiB and more) */
 		if (r != JDB_OK) return r;
 		r = jdb_lz_parse(in, n, cfg->chunk_bytes, cfg->chunk_len, prev, cfg->good, cfg->nice, cfg->chain, cfg->lazy,
 		                 cfg->dict_region / SEG, cfg->dict_pad, tok, seg_ntok, seg_hist, s);

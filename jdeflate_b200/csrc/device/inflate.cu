@@ -949,7 +949,7 @@ struct WideMem {
 	__align__(8) uint16_t E[WIDE_E];
 	__align__(8) uint8_t  H[WIDE_H];
 #ifdef WIDE_PROF
-	long long pt[12];               /* cycles per phase (thread 0), rounds, passes, sweeps, bytes */
+	long long pt[16];               /* cycles per phase (thread 0), rounds, passes, sweeps, bytes */
 	long long runs[16];             /* lanes that decoded in pass k */
 	long long pcyc[16];             /* cycles of pass k */
 	long long t_pass;
@@ -1188,6 +1188,7 @@ wide_round(const uint32_t* lit_, const uint32_t* dtab_, WideMem* w_)
 				left -= k;
 			}
 		}
+		WPROF(12);          /* warp 0: flat expand loop */
 		const uint32_t maxn = __reduce_max_sync(JDB_FULL_MASK, myn);
 		uint32_t x = x0;
 		for (uint32_t i = 0; i < maxn; i++) {
@@ -1209,8 +1210,9 @@ wide_round(const uint32_t* lit_, const uint32_t* dtab_, WideMem* w_)
 			x += len ? len : (i < myn ? 1u : 0u);
 		}
 	}
+	WPROF(13);          /* warp 0: long matches */
 	__syncthreads();
-	WPROF(4);           /* expand */
+	WPROF(4);           /* expand: waiting for the other warps */
 
 	/* ---- resolve ---- */
 	const uint32_t nquad = (a + nbytes + 3u) >> 2;
@@ -1969,7 +1971,7 @@ inflate_wide_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ 
 	}
 	if (lane == 0) { w->h_valid = 0; w->h_hi = 0; }
 #ifdef WIDE_PROF
-	if (lane == 0) { for (int k = 0; k < 12; k++) w->pt[k] = 0; for (int k = 0; k < 16; k++) { w->runs[k] = 0; w->pcyc[k] = 0; } w->t_last = clock64(); }
+	if (lane == 0) { for (int k = 0; k < 16; k++) w->pt[k] = 0; for (int k = 0; k < 16; k++) { w->runs[k] = 0; w->pcyc[k] = 0; } w->t_last = clock64(); }
 #endif
 	__syncwarp();
 	const jdb_inflate_item it = items[idx];
@@ -1997,6 +1999,7 @@ inflate_wide_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ 
 		printf("wide: kcycles of pass k, per round:");
 		for (int k = 0; k < 12; k++) printf(" %.1f", (double) w->pcyc[k] / 1e3 / w->pt[8]);
 		printf("\n");
+		printf("wide: expand of warp 0, kcycles/round: flat %.1f long %.1f\n", w->pt[12] / 1e3 / w->pt[8], w->pt[13] / 1e3 / w->pt[8]);
 		printf("wide: rounds %lld lanes/round %.1f passes/round %.2f sweeps/round %.2f bytes/round %.0f | kcycles/round: master %.1f stage %.1f decode %.1f chain %.1f expand %.1f resolve %.1f write %.1f\n",
 		       w->pt[8], (double) w->pt[7] / w->pt[8], (double) w->pt[9] / w->pt[8], (double) w->pt[10] / w->pt[8], (double) w->pt[11] / w->pt[8],
 		       w->pt[0] / 1e3 / w->pt[8], w->pt[1] / 1e3 / w->pt[8], w->pt[2] / 1e3 / w->pt[8], w->pt[3] / 1e3 / w->pt[8],

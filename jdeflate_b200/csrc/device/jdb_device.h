@@ -182,7 +182,10 @@ int jdb_inflate_chunks(const uint8_t* src_base, uint8_t* dst_base,
 /* links to the previous same-hash position (u16 distance, 0 = none), one per
  * input byte; `range` (divides chunk_bytes) is the work item of one warp */
 int jdb_lz_chain(const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint32_t range,
-                 const uint32_t* chunk_len, uint16_t* prev, jdb_stream s);
+                 const uint32_t* chunk_len, uint16_t* prev, uint16_t* heads, jdb_stream s);
+/* `heads` (jdb_lz_chain_heads_bytes, or NULL): scratch for the head tables the ranges leave behind;
+ * with it no range replays the 32 KiB in front of it (chain_fix_kernel links across ranges) */
+size_t jdb_lz_chain_heads_bytes(uint64_t n, uint32_t chunk_bytes);
 
 /* match search + parse: tokens of segment k at tok[k*JDB_SEG ...), their count
  * in seg_ntok[k], the 320-bin symbol histogram in seg_hist[k*320 ...) */

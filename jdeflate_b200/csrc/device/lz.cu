@@ -46,7 +46,9 @@
 #include "deflate.cuh"
 #include <stdlib.h>
 
+#ifndef HASH_BITS
 #define HASH_BITS      14
+#endif
 #define HASH_MUL       0x1e35a7bdu
 
 /* ---------------------------------------------------------------------------
@@ -121,7 +123,9 @@ chain_link_block(ChainSmem& S, uint32_t blk, unsigned lane)
 		const uint32_t stale = (rel0 + 0x8000u) & 0xffffu;
 		for (uint32_t i = lane; i < (1u << HASH_BITS); i += 32) {
 			uint32_t d = (rel0 - S.head[i]) & 0xffffu;
-			if (d >= WND) S.head[i] = (uint16_t) stale;
+			/* (d == 0: position rel0 itself is not in the table yet -- this is the "empty" value
+			 * of the start, 0x8000, which from here on would read as a link to position 32768) */
+			if (d >= WND || d == 0) S.head[i] = (uint16_t) stale;
 		}
 		__syncwarp();
 	}
@@ -166,7 +170,7 @@ chain_link_block(ChainSmem& S, uint32_t blk, unsigned lane)
 
 __global__ void __launch_bounds__(CH_THREADS)
 chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t range,
-             const uint32_t* __restrict__ chunk_len, uint16_t* __restrict__ prev)
+             const uint32_t* __restrict__ chunk_len, uint16_t* __restrict__ prev, uint16_t* __restrict__ heads)
 {
 	JDB_DYN_SMEM(smem_raw);
 	ChainSmem& S = *(ChainSmem*) smem_raw;
@@ -180,7 +184,10 @@ chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, u
 	if (r0 >= chunk1) return;                    /* ragged chunk: nothing in this range */
 	uint64_t r1 = r0 + range;
 	if (r1 > chunk1) r1 = chunk1;
-	const uint64_t start = r0 >= chunk0 + WND ? r0 - WND : chunk0;   /* warm-up start, multiple of SEG */
+	/* warm-up start, multiple of SEG.  With `heads` there is no warm-up: every range leaves its
+	 * head table behind and chain_fix_kernel links the first occurrences of a range to the last
+	 * ones of the range before it */
+	const uint64_t start = heads ? r0 : r0 >= chunk0 + WND ? r0 - WND : chunk0;
 
 	/* positions are handled relative to `start`; an entry holds the low 16
 	 * bits, "empty" is anything that decodes to a distance >= 32768 */
@@ -225,6 +232,59 @@ chain_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, u
 	}
 #undef CH_ROUND
 #undef LOADW
+	if (heads) {
+		/* distance from the end of the range back to the last position of every hash (0: none
+		 * inside the window); the last round ended with a barrier */
+		uint16_t* const hout = heads + (uint64_t) blockIdx.x * (1u << HASH_BITS);
+		for (uint32_t i = threadIdx.x; i < (1u << HASH_BITS); i += CH_THREADS) {
+			const uint32_t d = (span - S.head[i]) & 0xffffu;
+			hout[i] = (uint16_t) (d < WND ? d : 0u);
+		}
+	}
+}
+
+/*
+ * Second step of the chain build without warm-up: a position of range r that found no earlier
+ * position with its hash inside the range (link 0) is linked to the last such position of range
+ * r - 1, when that lies inside the window.  Only the first 32 KiB of a range can reach back.
+ */
+__global__ void __launch_bounds__(256)
+chain_fix_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes, uint32_t range,
+                 const uint32_t* __restrict__ chunk_len, uint16_t* __restrict__ prev, const uint16_t* __restrict__ heads)
+{
+	const uint64_t r0 = (uint64_t) blockIdx.x * range;
+	if (r0 >= n) return;
+	const uint64_t chunk0 = r0 / chunk_bytes * chunk_bytes;
+	if (r0 == chunk0) return;                    /* nothing in front of a chunk */
+	const uint64_t chunk1 = chunk_end(chunk_len, chunk0, chunk_bytes, n);
+	if (r0 >= chunk1) return;
+	uint64_t lim = r0 + WND < r0 + range ? r0 + WND : r0 + range;
+	if (chunk1 < 4) return;
+	if (lim > chunk1 - 3) lim = chunk1 - 3;      /* positions that have four bytes to hash */
+	const uint16_t* const H = heads + (uint64_t) (blockIdx.x - 1) * (1u << HASH_BITS);
+	/* eight positions per trip: their links (one 16-byte load; r0 is a multiple of SEG) and the
+	 * 11 bytes that hold their hashes (12 bytes from an 8-byte aligned address) -- no load depends
+	 * on a branch, so everything a trip needs is in flight at once */
+	for (uint64_t p8 = r0 + 8u * threadIdx.x; p8 < lim; p8 += 8u * 256u) {
+		const uint4 v = *(const uint4*) (prev + p8);
+		const uint2 b01 = *(const uint2*) (in + p8);
+		const uint32_t b2 = *(const uint32_t*) (in + p8 + 8);
+		const uint32_t lk[4] = { v.x, v.y, v.z, v.w };
+		const uint32_t by[4] = { b01.x, b01.y, b2, 0u };
+		uint32_t dend[8];
+#pragma unroll
+		for (uint32_t k = 0; k < 8; k++) {
+			const bool z = ((lk[k >> 1] >> (16u * (k & 1u))) & 0xffffu) == 0 && p8 + k < lim;
+			const uint32_t le = __funnelshift_r(by[k >> 2], by[(k >> 2) + 1], 8u * (k & 3u));
+			const uint32_t be = __byte_perm(le, 0, 0x0123);
+			dend[k] = z ? H[(be * HASH_MUL) >> (32 - HASH_BITS)] : 0u;
+		}
+#pragma unroll
+		for (uint32_t k = 0; k < 8; k++) {
+			const uint32_t d = (uint32_t) (p8 + k - r0) + dend[k];
+			if (dend[k] && d < WND) prev[p8 + k] = (uint16_t) d;
+		}
+	}
 }
 
 /* ---------------------------------------------------------------------------
@@ -1104,14 +1164,25 @@ lz_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk_bytes,
 /* ---- launchers ------------------------------------------------------------- */
 
 extern "C" int jdb_lz_chain(const uint8_t* in, uint64_t n, uint32_t chunk_bytes, uint32_t range,
-                            const uint32_t* chunk_len, uint16_t* prev, jdb_stream s)
+                            const uint32_t* chunk_len, uint16_t* prev, uint16_t* heads, jdb_stream s)
 {
 	if (n == 0) return JDB_OK;
 	const size_t smem = sizeof(ChainSmem);
 	JDB_CONFIGURE_SMEM(chain_kernel, smem);
 	const uint64_t items = (n + range - 1) / range;
-	JDB_LAUNCH(chain_kernel, dim3((unsigned) items), dim3(CH_THREADS), smem, s, in, n, chunk_bytes, range, chunk_len, prev);
-	return jdb_rt_check_launch("chain_kernel");
+	if (range < WND || range >= chunk_bytes) heads = NULL;      /* one range per chunk: nothing to link across */
+	JDB_LAUNCH(chain_kernel, dim3((unsigned) items), dim3(CH_THREADS), smem, s, in, n, chunk_bytes, range, chunk_len, prev, heads);
+	int r = jdb_rt_check_launch("chain_kernel");
+	if (r != JDB_OK || heads == NULL) return r;
+	JDB_LAUNCH(chain_fix_kernel, dim3((unsigned) items), dim3(256), 0, s, in, n, chunk_bytes, range, chunk_len, prev, (const uint16_t*) heads);
+	return jdb_rt_check_launch("chain_fix_kernel");
+}
+
+extern "C" size_t jdb_lz_chain_heads_bytes(uint64_t n, uint32_t chunk_bytes)
+{
+	/* one table per range of at least 64 KiB, and at least one range per chunk */
+	const uint64_t ranges = n / 65536u + (n + chunk_bytes - 1) / chunk_bytes + 2;
+	return (size_t) ranges * (1u << HASH_BITS) * 2u;
 }
 
 /* experiment switches, read once per process (JDB_LZ_*; -1 = the level's default) */

@@ -7,7 +7,7 @@ from support import Corpus, KIND_NAMES
 
 lib = C.CDLL(str(R / "tests/simt/_build/libjdeflate_emu.so"))
 lib.jdb_dev_alloc.restype = C.c_void_p; lib.jdb_dev_alloc.argtypes = [C.c_size_t]
-lib.jdb_lz_chain.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.jdb_lz_chain.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.jdb_lz_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p] + [C.c_uint32] * 6 + [C.c_void_p] * 4
 SEG = 8192
 
@@ -17,7 +17,7 @@ def run(data: bytes, chunk=262144, rng=131072, good=16, nice=16, chain=48, lazy=
     din = lib.jdb_dev_alloc(npad); C.memmove(din, data, n)
     prev = lib.jdb_dev_alloc(npad * 2); tok = lib.jdb_dev_alloc(npad * 4)
     ntok = lib.jdb_dev_alloc(nseg * 4 + 64); hist = lib.jdb_dev_alloc(nseg * 320 * 4)
-    assert lib.jdb_lz_chain(din, n, chunk, rng, None, prev, None) == 0
+    assert lib.jdb_lz_chain(din, n, chunk, rng, None, prev, None, None) == 0
     assert lib.jdb_lz_parse(din, n, chunk, None, prev, good, nice, chain, lazy, 0, 0, tok, ntok, hist, None) == 0
     prev_a = np.frombuffer((C.c_uint16 * n).from_address(prev), np.uint16)
     tok_a = np.frombuffer((C.c_uint32 * (nseg * SEG)).from_address(tok), np.uint32)
