@@ -302,3 +302,60 @@ def test_preset_dictionary_stream_larger_than_a_chunk_against_the_reference(lib,
             finally:
                 s.close()
     assert sizes["ours"] <= RATIO_TOLERANCE * sizes["ref"], sizes
+
+
+def test_chain_links_equal_the_exact_model(emu, corpus):
+    """chain_kernel + chain_fix_kernel against a plain restatement of what a link is (the reference's
+    hash insert, src/deflator.c:2402-2428: every position points at the previous position with the
+    same hash of its 4 bytes, inside the window and inside its chunk): with and without the head
+    tables that replace the warm-up replay, ranges of 64 and 128 KiB, a ragged tail.  Pins two things
+    that went wrong once: the start value of the head table reading as a link to position 32768, and
+    the links across range boundaries."""
+    import ctypes as C
+    import numpy as np
+    lib = emu.lib
+    lib.jdb_dev_alloc.restype = C.c_void_p
+    lib.jdb_dev_alloc.argtypes = [C.c_size_t]
+    lib.jdb_lz_chain.restype = C.c_int
+    lib.jdb_lz_chain.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.jdb_lz_chain_heads_bytes.restype = C.c_size_t
+    lib.jdb_lz_chain_heads_bytes.argtypes = [C.c_uint64, C.c_uint32]
+
+    def links(data, chunk, rng, use_heads):
+        n = len(data)
+        npad = (n + 8191) // 8192 * 8192 + 64
+        din = lib.jdb_dev_alloc(npad)
+        C.memset(din, 0, npad)
+        C.memmove(din, data, n)
+        prev = lib.jdb_dev_alloc(npad * 2)
+        C.memset(prev, 0, npad * 2)
+        heads = lib.jdb_dev_alloc(lib.jdb_lz_chain_heads_bytes(n, chunk)) if use_heads else None
+        assert lib.jdb_lz_chain(din, n, chunk, rng, None, prev, heads, None) == 0
+        return np.frombuffer((C.c_uint16 * n).from_address(prev), np.uint16).astype(np.int64)
+
+    def model(data, chunk):
+        d = np.frombuffer(data, np.uint8).astype(np.uint64)
+        n = len(d)
+        be = (d[:-3] << 24) | (d[1:-2] << 16) | (d[2:-1] << 8) | d[3:]
+        h = ((be * 0x1e35a7bd) & 0xffffffff) >> (32 - 14)
+        want = np.zeros(n, np.int64)
+        last = {}
+        for p in range(n - 3):
+            if p % chunk == 0:
+                last = {}
+            if p + 3 >= min((p // chunk + 1) * chunk, n):
+                continue
+            q = last.get(int(h[p]))
+            if q is not None and p - q < 32768:
+                want[p] = p - q
+            last[int(h[p])] = p
+        return want
+
+    for kind, n in ((0, 262144 + 131072 + 5000), (2, 200000), (4, 70000)):
+        data = corpus.fill(kind, n, offset=99)
+        for chunk, rng in ((262144, 65536), (524288, 131072)):
+            want = model(data, chunk)
+            for use_heads in (False, True):
+                got = links(data, chunk, rng, use_heads)
+                bad = np.nonzero(got != want)[0]
+                assert len(bad) == 0, (kind, n, chunk, rng, use_heads, bad[:5], got[bad[:5]], want[bad[:5]])
