@@ -1951,7 +1951,7 @@ inflate_batch_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__
 __global__ void __launch_bounds__(WIDE_LANES, 1)
 inflate_wide_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ dst_base,
                     const jdb_inflate_item* __restrict__ items, jdb_inflate_result* __restrict__ results,
-                    jdb_inflate_state* states, uint32_t final)
+                    jdb_inflate_state* states, uint32_t format, uint32_t final)
 {
 	JDB_DYN_SMEM(smem_raw);
 	WarpMem* m = (WarpMem*) smem_raw;
@@ -1984,10 +1984,41 @@ inflate_wide_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ 
 	s.count_only = 0;
 	s.stop_marker = 0;
 	s.st = states ? states + idx : NULL;
-	inflate_stream<true>(m, s, w);
+	/* container framing as in inflate_batch_kernel (src/zstrm.c:510-565) */
+	uint32_t zerr = 0, head = 0;
+	if (format == JDB_FMT_ZLIB) {
+		if (s.src_len < 2) zerr = JDB_ZERR_BADDATA;
+		else {
+			const uint32_t cmf = s.src[0], flg = s.src[1];
+			if ((cmf & 15u) != 8 || (cmf >> 4) > 7) zerr = JDB_ZERR_BADDATA;
+			else if (flg & 0x20u) zerr = JDB_ZERR_MISSINGDICT;
+			head = 2;
+		}
+	}
 	jdb_inflate_result r;
-	r.status = s.status; r.error = s.error; r.zerror = 0; r.checksum = 0;
-	r.consumed = s.consumed; r.produced = s.out;
+	r.status = ST_ERROR; r.error = 0; r.zerror = zerr; r.checksum = 0;
+	r.consumed = 0; r.produced = 0;
+	if (!zerr) {
+		s.src += head;
+		s.src_len -= head;
+		inflate_stream<true>(m, s, w);
+		r.status = s.status;
+		r.error = s.error;
+		r.consumed = s.consumed + head;
+		r.produced = s.out;
+		if (format == JDB_FMT_ZLIB && s.status == ST_OK) {
+			const uint32_t ad = warp_adler32(s.dst, s.out);
+			r.checksum = ad;
+			if (r.consumed + 4 > it.src_len) {
+				r.zerror = JDB_ZERR_BADDATA;
+			} else {
+				const uint8_t* t = src_base + it.src_off + r.consumed;
+				const uint32_t want = ((uint32_t) t[0] << 24) | ((uint32_t) t[1] << 16) | ((uint32_t) t[2] << 8) | t[3];
+				if (want != ad) r.zerror = JDB_ZERR_CHECKSUM;
+				r.consumed += 4;
+			}
+		}
+	}
 	if (lane == 0) {
 		results[idx] = r;
 		w->cmd = 0;
@@ -2011,13 +2042,13 @@ inflate_wide_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ 
 
 extern "C" int jdb_inflate_wide(const uint8_t* src_base, uint8_t* dst_base,
                                 const jdb_inflate_item* items, jdb_inflate_result* results,
-                                jdb_inflate_state* states, uint32_t count, uint32_t final, jdb_stream s)
+                                jdb_inflate_state* states, uint32_t count, uint32_t format, uint32_t final, jdb_stream s)
 {
 	if (count == 0) return JDB_OK;
 	const size_t smem = ((sizeof(WarpMem) + 15u) & ~(size_t) 15u) + sizeof(WideMem);
 	JDB_CONFIGURE_SMEM(inflate_wide_kernel, smem);
 	JDB_LAUNCH(inflate_wide_kernel, dim3(count), dim3(WIDE_LANES), smem, s,
-	           src_base, dst_base, items, results, states, final);
+	           src_base, dst_base, items, results, states, format, final);
 	return jdb_rt_check_launch("inflate_wide_kernel");
 }
 

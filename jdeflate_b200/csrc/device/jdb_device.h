@@ -158,12 +158,13 @@ int jdb_inflate_batch(const uint8_t* src_base, uint8_t* dst_base,
 
 /*
  * The same for streams that deserve a whole CTA each (inflate_wide_kernel): one resumable raw
- * DEFLATE stream per item, `count` CTAs.  This is what inflator_inflate runs for a stream
- * that carries no chunk markers.
+ * DEFLATE (or zlib) stream per item, `count` CTAs.  This is what inflator_inflate runs for a
+ * stream that carries no chunk markers, and jdb200_inflate_batch for a batch of fewer streams
+ * than the device has SMs.
  */
 int jdb_inflate_wide(const uint8_t* src_base, uint8_t* dst_base,
                      const jdb_inflate_item* items, jdb_inflate_result* results,
-                     jdb_inflate_state* states, uint32_t count, uint32_t final, jdb_stream s);
+                     jdb_inflate_state* states, uint32_t count, uint32_t format, uint32_t final, jdb_stream s);
 
 /* chunk discovery for the parallel decode of one large stream (inflate.cu) */
 int jdb_marker_scan(const uint8_t* src, uint64_t n, uint32_t* ends, uint32_t max_ends,

@@ -17,6 +17,7 @@ static __thread struct {
 	uint32_t* counter;
 	int ready;
 	int device;                                      /* where stream and buffers live */
+	int narrow;                                      /* JDB200_INFLATE_NARROW=1: one warp per stream whatever the count */
 } bt;
 
 static int
@@ -51,6 +52,10 @@ batch_prepare(void)
 		return JDB_ENOMEM;
 	}
 	bt.device = jdb_rt_current_device();
+	{
+		const char* e = getenv("JDB200_INFLATE_NARROW");
+		bt.narrow = e != NULL && e[0] == '1';
+	}
 	bt.ready = 1;
 	return JDB_OK;
 }
@@ -117,8 +122,16 @@ jdb200_inflate_batch(const uint8* source, uint8* target,
 		dresults = (jdb_inflate_result*) bt.results.ptr;
 	}
 
-	r = jdb_inflate_batch(dsrc, ddst, ditems, dresults, NULL, (uint32_t) count,
-	                      format == JDB200_ZLIB ? JDB_FMT_ZLIB : JDB_FMT_RAW, 1, bt.counter, bt.stream);
+	/* fewer streams than SMs: a thread block per stream (inflate_wide_kernel, ~7x a lone warp on a long
+	 * stream) -- one warp per stream could not fill the device anyway */
+	if (count <= (uintxx) jdb_rt_sm_count() && !bt.narrow) {
+		r = jdb_inflate_wide(dsrc, ddst, ditems, dresults, NULL, (uint32_t) count,
+		                     format == JDB200_ZLIB ? JDB_FMT_ZLIB : JDB_FMT_RAW, 1, bt.stream);
+	}
+	else {
+		r = jdb_inflate_batch(dsrc, ddst, ditems, dresults, NULL, (uint32_t) count,
+		                      format == JDB200_ZLIB ? JDB_FMT_ZLIB : JDB_FMT_RAW, 1, bt.counter, bt.stream);
+	}
 	if (r != JDB_OK) {
 		return r;
 	}

@@ -882,7 +882,7 @@ inflator_inflate(TInflator* state, uint32 final)
 		         ? jdb_inflate_batch(PRVT->inq.ptr, dst, D_ITEM(PRVT), D_RESULT(PRVT), PRVT->dstate, 1,
 		                             JDB_FMT_RAW, (uint32_t) (PBLC->finalinput && absorbed_all),
 		                             D_COUNTER(PRVT), PRVT->stream)
-		         : jdb_inflate_wide(PRVT->inq.ptr, dst, D_ITEM(PRVT), D_RESULT(PRVT), PRVT->dstate, 1,
+		         : jdb_inflate_wide(PRVT->inq.ptr, dst, D_ITEM(PRVT), D_RESULT(PRVT), PRVT->dstate, 1, JDB_FMT_RAW,
 		                            (uint32_t) (PBLC->finalinput && absorbed_all), PRVT->stream)) != JDB_OK ||
 		    jdb_copy_async(res, D_RESULT(PRVT), sizeof(*res), PRVT->stream) != JDB_OK ||
 		    jdb_stream_sync(PRVT->stream) != JDB_OK) {

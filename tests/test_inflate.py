@@ -438,3 +438,48 @@ def test_wide_and_narrow_decoders_agree_on_device_targets(jd, corpus):
                 assert int(back[:off].sum()) == 0 and int(back[off + len(d):].sum()) == 0
         finally:
             os.environ.pop("JDB200_INFLATE_NARROW", None)
+
+
+def test_small_batches_take_a_thread_block_per_stream(lib, oracle, corpus, monkeypatch):
+    """jdb200_inflate_batch with fewer streams than SMs runs inflate_wide_kernel (one CTA per stream), with the
+    zlib framing of the batch kernel: good, damaged, truncated and over-long members, a bad header, a preset
+    dictionary flag, a target that is too small -- every result field as the one-warp kernel reports it, and
+    as the oracle decides for the raw streams."""
+    monkeypatch.setenv("JDB_EMU_SMS", "148")        # the emulator's device has 4 SMs by default; a B200 has 148
+    d_long, _ = _mixed_stream(corpus, 700_000)
+    recs = [b"", b"x", corpus.fill(0, 5000, offset=1), corpus.fill(2, 70000, offset=2), d_long, corpus.json_record(7)]
+    good = [zlib.compress(r, 6) for r in recs]
+    bad_sum = bytearray(good[3]); bad_sum[-1] ^= 1
+    bad_data = bytearray(good[4]); bad_data[len(bad_data) // 2] ^= 0x10
+    bad_hdr = bytearray(good[2]); bad_hdr[0] = 0x79
+    fdict = bytearray(good[2]); fdict[1] |= 0x20
+    streams = good + [bytes(bad_sum), bytes(bad_data), good[4][: len(good[4]) // 3], bytes(bad_hdr), bytes(fdict), good[3], b"\x78"]
+    want_out = recs + [recs[3], None, None, None, None, None, None]
+    caps = [len(r) for r in recs] + [len(recs[3]), len(recs[4]), len(recs[4]), 5000, 5000, 1000, 10]
+    outs, res = lib.inflate_batch_bytes(streams, caps, fmt=api.JDB200_ZLIB)
+    for i in range(len(recs)):
+        q = res[i]
+        assert (q.status, q.error, q.zerror) == (api.OK, 0, 0), i
+        assert outs[i] == recs[i] and q.srcused == len(streams[i]) and q.checksum == zlib.adler32(recs[i]), i
+    k = len(recs)
+    assert (res[k].status, res[k].zerror) == (api.OK, 4) and outs[k] == recs[3]            # checksum mismatch
+    assert res[k + 2].status == api.ERROR and res[k + 2].error == api.INFLT_EINPUTEND     # truncated
+    assert res[k + 3].zerror == 3 and res[k + 4].zerror == 6 and res[k + 6].zerror == 3   # header, FDICT, 1 byte
+    assert res[k + 5].status == api.TGTEXHSTD and outs[k + 5] == recs[3][:1000]
+    # the same batch through the one-warp kernel (a device with a single SM has fewer SMs than streams)
+    monkeypatch.setenv("JDB_EMU_SMS", "1")
+    outs1, res1 = lib.inflate_batch_bytes(streams, caps, fmt=api.JDB200_ZLIB)
+    fields = ("status", "error", "zerror", "checksum", "srcused", "tgtused")
+    for i, (a, b) in enumerate(zip(res, res1)):
+        assert [getattr(a, f) for f in fields] == [getattr(b, f) for f in fields], i
+        assert outs[i] == outs1[i], i
+    # raw streams against the oracle
+    monkeypatch.setenv("JDB_EMU_SMS", "148")
+    raw = [z[2:-4] for z in good] + [bytes(bad_data)[2:-4], good[4][2: len(good[4]) // 3]]
+    rcaps = [len(r) for r in recs] + [len(recs[4]), len(recs[4])]
+    outs, res = lib.inflate_batch_bytes(raw, rcaps, fmt=api.JDB200_RAW)
+    for i, (z, cap) in enumerate(zip(raw, rcaps)):
+        want = oracle.inflate(z, cap, final=True)
+        assert (res[i].status, res[i].error) == (want[0], want[1]), i
+        if want[0] == api.OK:
+            assert outs[i] == want[2] and res[i].srcused == want[3], i
