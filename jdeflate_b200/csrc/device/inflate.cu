@@ -920,7 +920,10 @@ lane_lead_in(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, u
 
 struct WideMem {
 	/* command block: written by the master before the command barrier */
-	uint32_t cmd;                   /* 0: leave, 1: round, 2: copy (stored block) */
+	uint32_t cmd;                   /* 0: leave, 1: round, 2: copy (stored block), 3: Adler-32 of the output */
+	uint64_t ad_n;                  /* Adler-32: bytes at cp_src; partial sums per warp, result */
+	unsigned long long ad_a[WIDE_WARPS], ad_b[WIDE_WARPS];
+	uint32_t ad_result;
 	const uint8_t* cp_src;          /* copy: source, target, bytes */
 	uint8_t* cp_dst;
 	uint32_t cp_n;
@@ -1300,6 +1303,43 @@ wide_copy(WideMem* w_)
 		const uint32_t lo = __ldg(pw + i);
 		const uint32_t hi = sh ? __ldg(pw + i + 1) : 0u;      /* never past the word of the last byte */
 		dw[i] = __funnelshift_r(lo, hi, sh);
+	}
+	__syncthreads();
+}
+
+/* all threads of the CTA: Adler-32 of the n bytes at cp_src (the decoded stream, read back through L2);
+ * warp_adler32 on 512 threads -- a lone warp took as long over the checksum of a long stream as the CTA
+ * over decoding it */
+static __device__ __noinline__ void
+wide_adler(WideMem* w_)
+{
+	WideMem* const w = jdb_pin_shared(w_);
+	const unsigned gl = threadIdx.x, lane = jdb_lane(), wp = jdb_warp();
+	const uint8_t* const p = w->cp_src;
+	const uint64_t n = w->ad_n;
+	unsigned long long a = 0, b = 0;
+	uint32_t k = 0;
+#pragma unroll 8
+	for (uint64_t i = gl; i < n; i += WIDE_LANES) {
+		const uint32_t v = __ldcg(p + i);
+		a += v;
+		b += (unsigned long long) (n - i) * v;
+		if (++k == 65536u) { b %= 65521u; k = 0; }      /* (n - i) * v < 2^40 for the sizes a batch item can have */
+	}
+	a %= 65521u;
+	b %= 65521u;
+	for (int o = 16; o; o >>= 1) {
+		a += __shfl_xor_sync(JDB_FULL_MASK, a, o);
+		b += __shfl_xor_sync(JDB_FULL_MASK, b, o);
+	}
+	if (lane == 0) { w->ad_a[wp] = a; w->ad_b[wp] = b; }
+	__syncthreads();
+	if (gl == 0) {
+		unsigned long long sa = 0, sb = 0;
+		for (uint32_t q = 0; q < WIDE_WARPS; q++) { sa += w->ad_a[q]; sb += w->ad_b[q]; }
+		sa = (1 + sa) % 65521u;                        /* start value 1: a = 1 + sum, b = n * 1 + weighted sum */
+		sb = (n % 65521u + sb % 65521u) % 65521u;
+		w->ad_result = (uint32_t) ((sb << 16) | sa);
 	}
 	__syncthreads();
 }
@@ -1965,6 +2005,7 @@ inflate_wide_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ 
 			const uint32_t cmd = w->cmd;
 			if (cmd == 0) break;
 			if (cmd == 2) wide_copy(w);
+			else if (cmd == 3) wide_adler(w);
 			else wide_round(m->lit, m->dist, w);
 		}
 		return;
@@ -2007,7 +2048,14 @@ inflate_wide_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ 
 		r.consumed = s.consumed + head;
 		r.produced = s.out;
 		if (format == JDB_FMT_ZLIB && s.status == ST_OK) {
-			const uint32_t ad = warp_adler32(s.dst, s.out);
+			if (lane == 0) {
+				w->cmd = 3;
+				w->cp_src = s.dst;
+				w->ad_n = s.out;
+			}
+			__syncthreads();
+			wide_adler(w);
+			const uint32_t ad = w->ad_result;
 			r.checksum = ad;
 			if (r.consumed + 4 > it.src_len) {
 				r.zerror = JDB_ZERR_BADDATA;
