@@ -753,7 +753,8 @@ lane_decode(const uint32_t* inbuf, const uint32_t* lit, const uint32_t* dtab, ui
 #define WIDE_WARPS       16
 #endif
 #ifndef WIDE_LEAD
-#define WIDE_LEAD        0u         /* bits a lane decodes in front of its subsequence before its first guess */
+#define WIDE_LEAD        0u         /* bits a lane decodes in front of its subsequence before its first guess; 0 = off:
+                                    * measured, a lead-in is pass 1 under another name; experiment switch */
 #endif
 #ifndef WIDE_MAXPASS
 #define WIDE_MAXPASS     12
